@@ -1,0 +1,65 @@
+# Top-level build: product library (CUDA, sm_100a) + test oracle (gcc).  `make -j8`.
+#   fastlanes_b200/lib/libfastlanes_b200.so   — the C-ABI product (include/fastlanes_b200.h)
+#   oracle/_build/libfl_oracle.so             — CPU oracle (test infrastructure; never linked by the product)
+NVCC ?= /usr/local/cuda/bin/nvcc
+ARCH := -gencode arch=compute_100a,code=sm_100a
+NVFLAGS ?= -std=c++17 -O3 -lineinfo $(ARCH) -Xcompiler -fPIC -Xcompiler -fvisibility=hidden \
+           --expt-relaxed-constexpr
+SRC := fastlanes_b200/csrc
+OBJ := build/obj
+LIB := fastlanes_b200/lib/libfastlanes_b200.so
+TYPES := 8 16 32 64
+PARTS := 0 1 2
+HDRS := $(SRC)/fl_device.cuh $(SRC)/fl_kernels.cuh $(SRC)/fl_internal.h include/fastlanes_b200.h
+
+CODEC_OBJS := $(foreach t,$(TYPES),$(foreach p,$(PARTS),$(OBJ)/codec_u$(t)_p$(p).o))
+OBJS := $(CODEC_OBJS) $(OBJ)/fl_misc.o $(OBJ)/fl_api.o
+
+all: lib oracle
+lib: $(LIB)
+oracle:
+	$(MAKE) -C oracle
+
+$(OBJ):
+	mkdir -p $(OBJ) fastlanes_b200/lib
+
+define CODEC_RULE
+$(OBJ)/codec_u$(1)_p$(2).o: $(SRC)/fl_codec_inst.cu $(HDRS) | $(OBJ)
+	$(NVCC) $(NVFLAGS) -DFLB_TBITS=$(1) -DFLB_PART=$(2) -c $$< -o $$@
+endef
+$(foreach t,$(TYPES),$(foreach p,$(PARTS),$(eval $(call CODEC_RULE,$(t),$(p)))))
+
+$(OBJ)/fl_misc.o: $(SRC)/fl_misc.cu $(HDRS) | $(OBJ)
+	$(NVCC) $(NVFLAGS) -c $< -o $@
+$(OBJ)/fl_api.o: $(SRC)/fl_api.cu $(HDRS) | $(OBJ)
+	$(NVCC) $(NVFLAGS) -c $< -o $@
+
+$(LIB): $(OBJS)
+	$(NVCC) -shared $(ARCH) -o $@ $(OBJS) -cudart static
+
+tools/kbench: tools/kbench.cu $(HDRS)
+	$(NVCC) $(NVFLAGS) -I$(SRC) -o $@ $< -cudart static
+
+clean:
+	rm -rf build fastlanes_b200/lib tools/kbench
+	$(MAKE) -C oracle clean
+
+.PHONY: all lib oracle clean
+
+# kernel micro-benchmark variants: make kbench-variants
+KB := build/kbench
+$(KB):
+	mkdir -p $(KB)
+$(KB)/kb_base: tools/kbench.cu $(HDRS) | $(KB)
+	$(NVCC) $(NVFLAGS) -I$(SRC) -o $@ $< -cudart static
+$(KB)/kb_%: tools/kbench.cu $(HDRS) | $(KB)
+	$(NVCC) $(NVFLAGS) -I$(SRC) $(KBFLAGS_$*) -o $@ $< -cudart static
+KBFLAGS_st1 := -DFLB_ST_MODE=1
+KBFLAGS_st2 := -DFLB_ST_MODE=2
+KBFLAGS_ld1 := -DFLB_LD_MODE=1
+KBFLAGS_ld3 := -DFLB_LD_MODE=3
+KBFLAGS_pf4 := -DFLB_PREFETCH=4
+KBFLAGS_pf16 := -DFLB_PREFETCH=16
+KBFLAGS_t128 := -DFLB_THREADS=128
+KBFLAGS_t512 := -DFLB_THREADS=512
+kbench-variants: $(KB)/kb_base $(KB)/kb_st1 $(KB)/kb_st2 $(KB)/kb_ld1 $(KB)/kb_ld3 $(KB)/kb_pf4 $(KB)/kb_pf16 $(KB)/kb_t128 $(KB)/kb_t512

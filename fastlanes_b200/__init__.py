@@ -1,0 +1,332 @@
+"""fastlanes_b200 — host-side mirror of the spiraldb/fastlanes trait surface over the C-ABI library.
+
+The reference's public API is four traits implemented for u8/u16/u32/u64 (src/lib.rs:17-32):
+
+    BitPacking  pack / unchecked_pack / unpack / unchecked_unpack / unpack_single / unchecked_unpack_single
+                (src/bitpacking.rs:16-59)
+    FoR         for_pack / unfor_pack                      (src/ffor.rs:4-18)
+    Delta       delta / undelta / undelta_pack             (src/delta.rs:6-17)
+    Transpose   transpose / untranspose                    (src/transpose.rs:4-7)
+
+This module keeps those names and argument orders, with the const-generic `W` as the leading `width`
+argument (as in the reference's own `unchecked_*` family), batched over any whole number of 1024-value
+blocks.  Where the reference panics (width > T, wrong slice lengths, index >= 1024) a FastLanesError is
+raised.  Arguments are either
+
+  * numpy arrays (host memory)  -> the `fl_host_*` entry points: H2D, sm_100a kernels, D2H; or
+  * torch CUDA tensors          -> the stream-ordered device entry points on torch's current stream.
+
+Every value is computed by the CUDA library; there is no CPU implementation in this package.
+"""
+from __future__ import annotations
+
+import ctypes
+
+import numpy as np
+
+from . import _lib
+from ._lib import FastLanesError, LIB_PATH, exported_symbols  # noqa: F401
+
+FL_ORDER = (0, 4, 2, 6, 1, 5, 3, 7)  # src/lib.rs:22
+
+__all__ = ["BitPacking", "FoR", "Delta", "Transpose", "FastLanes", "FastLanesError", "FL_ORDER",
+           "packed_len", "version", "device_count", "host_configure", "pinned_empty", "shutdown"]
+
+
+class FastLanes:
+    """`trait FastLanes { const T; const LANES }` (src/lib.rs:24-27) for an element bit size."""
+
+    def __init__(self, tbits: int):
+        if tbits not in (8, 16, 32, 64):
+            raise FastLanesError(_lib.FL_ERR_LEN, f"unsupported element size {tbits}")
+        self.T = tbits
+        self.LANES = 1024 // tbits
+
+
+def packed_len(tbits: int, width: int) -> int:
+    """Elements in one packed block: 1024 * W / T (src/bitpacking.rs:19)."""
+    return 1024 * width // tbits
+
+
+def version() -> str:
+    return _lib.lib().fl_version().decode()
+
+
+def device_count() -> int:
+    return _lib.lib().fl_device_count()
+
+
+def host_configure(chunk_blocks: int = 0, n_streams: int = 0) -> None:
+    _lib.check(_lib.lib().fl_host_configure(chunk_blocks, n_streams))
+
+
+def shutdown() -> None:
+    _lib.check(_lib.lib().fl_shutdown())
+
+
+def pinned_empty(n: int, dtype) -> np.ndarray:
+    """A page-locked numpy array (fl_host_alloc); keeps the allocation alive for the array's lifetime."""
+    dt = np.dtype(dtype)
+    p = ctypes.c_void_p()
+    _lib.check(_lib.lib().fl_host_alloc(ctypes.byref(p), max(1, n * dt.itemsize)))
+    buf = (ctypes.c_uint8 * (n * dt.itemsize)).from_address(p.value)
+    arr = np.frombuffer(buf, dtype=dt, count=n)
+
+    class _Owner:
+        def __init__(self, ptr):
+            self.ptr = ptr
+
+        def __del__(self):
+            try:
+                _lib.lib().fl_host_free(self.ptr)
+            except Exception:
+                pass
+
+    owner = _Owner(p.value)
+    # tie the owner to the base buffer so that views keep it alive
+    buf._fl_owner = owner
+    return arr
+
+
+# ---- argument plumbing ---------------------------------------------------------------------------
+
+def _is_torch(x) -> bool:
+    return type(x).__module__.startswith("torch")
+
+
+class _Arg:
+    __slots__ = ("ptr", "n", "tbits", "device")
+
+    def __init__(self, x, what: str):
+        if _is_torch(x):
+            if not x.is_cuda:
+                raise FastLanesError(_lib.FL_ERR_NULL, f"{what}: torch tensors must live on a CUDA device")
+            if not x.is_contiguous():
+                raise FastLanesError(_lib.FL_ERR_LEN, f"{what}: tensor must be contiguous")
+            self.ptr, self.n, self.tbits, self.device = x.data_ptr(), x.numel(), x.element_size() * 8, x.device.index
+        elif isinstance(x, np.ndarray):
+            if not x.flags.c_contiguous:
+                raise FastLanesError(_lib.FL_ERR_LEN, f"{what}: array must be C-contiguous")
+            if x.dtype.kind != "u":
+                raise FastLanesError(_lib.FL_ERR_LEN, f"{what}: unsigned integer dtype required")
+            self.ptr, self.n, self.tbits, self.device = x.ctypes.data, x.size, x.dtype.itemsize * 8, None
+        else:
+            raise FastLanesError(_lib.FL_ERR_NULL, f"{what}: numpy array or torch CUDA tensor required")
+
+
+def _same_space(*args: _Arg) -> bool:
+    dev = {a.device is not None for a in args}
+    if len(dev) != 1:
+        raise FastLanesError(_lib.FL_ERR_NULL, "all buffers must be host arrays or all CUDA tensors")
+    tb = {a.tbits for a in args}
+    if len(tb) != 1:
+        raise FastLanesError(_lib.FL_ERR_LEN, "all buffers must share one element type")
+    return dev.pop()
+
+
+def _stream():
+    import torch
+
+    return ctypes.c_void_p(torch.cuda.current_stream().cuda_stream)
+
+
+def _check_width(width: int, tbits: int):
+    if width < 0 or width > tbits:
+        # the reference: compile error for const W (bitpacking.rs:10-12), unreachable!() at run time (:93)
+        raise FastLanesError(_lib.FL_ERR_WIDTH, f"Unsupported width: {width}")
+
+
+def _n_blocks_unpacked(a: _Arg, what: str) -> int:
+    if a.n % 1024:
+        raise FastLanesError(_lib.FL_ERR_LEN, f"{what} buffer must be a whole number of 1024-element blocks")
+    return a.n // 1024
+
+
+def _expect(a: _Arg, n: int, what: str):
+    if a.n != n:
+        raise FastLanesError(_lib.FL_ERR_LEN, f"{what} buffer must hold {n} elements, got {a.n}")
+
+
+def _call(base, tbits, on_device, *args):
+    name = base if on_device else base.replace("fl_", "fl_host_", 1)
+    if on_device:
+        args = args + (_stream(),)
+    _lib.check(_lib.fn(name, tbits)(*args))
+
+
+class BitPacking:
+    """src/bitpacking.rs:16-59."""
+
+    @staticmethod
+    def pack(width: int, input, output) -> None:
+        """`pack::<W>(input: &[T; 1024], output: &mut [T; 1024*W/T])` (:19, impl :65-74), batched."""
+        i, o = _Arg(input, "input"), _Arg(output, "output")
+        dev = _same_space(i, o)
+        _check_width(width, i.tbits)
+        n = _n_blocks_unpacked(i, "Input")
+        _expect(o, n * packed_len(i.tbits, width), "Output")  # :78
+        _call("fl_pack", i.tbits, dev, width, n, i.ptr, o.ptr)
+
+    unchecked_pack = pack  # :30 (impl :76-96): same runtime-width dispatch; lengths ARE checked here
+
+    @staticmethod
+    def unpack(width: int, input, output) -> None:
+        """`unpack::<W>(input: &[T; 1024*W/T], output: &mut [T; 1024])` (:33, impl :98-107), batched."""
+        i, o = _Arg(input, "input"), _Arg(output, "output")
+        dev = _same_space(i, o)
+        _check_width(width, o.tbits)
+        n = _n_blocks_unpacked(o, "Output")
+        _expect(i, n * packed_len(o.tbits, width), "Input")  # :111
+        _call("fl_unpack", o.tbits, dev, width, n, i.ptr, o.ptr)
+
+    unchecked_unpack = unpack  # :44 (impl :109-129)
+
+    @staticmethod
+    def unpack_single(width: int, packed, index: int):
+        """`unpack_single::<W>(packed, index) -> T` (:47, impl :132-179) on ONE packed block (host array)."""
+        p = _Arg(packed, "packed")
+        if p.device is not None:
+            raise FastLanesError(_lib.FL_ERR_NULL, "unpack_single takes a host array; use unpack_gather for tensors")
+        _check_width(width, p.tbits)
+        _expect(p, packed_len(p.tbits, width), "Input")  # :185
+        if not 0 <= index < 1024:
+            raise FastLanesError(_lib.FL_ERR_INDEX, f"Index must be less than 1024, got {index}")  # :152
+        out = np.zeros(1, dtype=packed.dtype)
+        _lib.check(_lib.fn("fl_host_unpack_single", p.tbits)(width, p.ptr, index, out.ctypes.data))
+        return out[0]
+
+    unchecked_unpack_single = unpack_single  # :58 (impl :181-200)
+
+    @staticmethod
+    def unpack_gather(width: int, packed, global_index, output) -> None:
+        """Batched unpack_single: output[i] = value at block global_index[i]//1024, index global_index[i]%1024."""
+        p, g, o = _Arg(packed, "packed"), _Arg(global_index, "global_index"), _Arg(output, "output")
+        if g.tbits != 64:
+            raise FastLanesError(_lib.FL_ERR_LEN, "global_index must be uint64")
+        dev = _same_space(p, o)
+        if (g.device is not None) != dev:
+            raise FastLanesError(_lib.FL_ERR_NULL, "all buffers must be host arrays or all CUDA tensors")
+        _check_width(width, p.tbits)
+        per = packed_len(p.tbits, width)
+        if per and p.n % per:
+            raise FastLanesError(_lib.FL_ERR_LEN, "packed buffer must be a whole number of packed blocks")
+        n_blocks = p.n // per if per else (1 << 40)
+        _expect(o, g.n, "Output")
+        if dev:
+            import torch
+
+            flag = torch.zeros(1, dtype=torch.int32, device=packed.device)
+            _lib.check(_lib.fn("fl_unpack_gather", p.tbits)(width, n_blocks, p.ptr, g.ptr, g.n, o.ptr,
+                                                            flag.data_ptr(), _stream()))
+            if int(flag.item()):
+                raise FastLanesError(_lib.FL_ERR_INDEX, "index out of range")
+        else:
+            _lib.check(_lib.fn("fl_host_unpack_gather", p.tbits)(width, n_blocks, p.ptr, g.ptr, g.n, o.ptr))
+
+
+def _ref_value(reference, tbits: int) -> int:
+    return int(reference) & ((1 << tbits) - 1)
+
+
+class FoR:
+    """src/ffor.rs:4-18."""
+
+    @staticmethod
+    def for_pack(width: int, input, reference, output) -> None:
+        """`for_pack::<W>(input, reference, output)` (:5-10, impl :24-36).  `reference`: a scalar, or (CUDA
+        tensors only) one reference per block."""
+        i, o = _Arg(input, "input"), _Arg(output, "output")
+        dev = _same_space(i, o)
+        _check_width(width, i.tbits)
+        n = _n_blocks_unpacked(i, "Input")
+        _expect(o, n * packed_len(i.tbits, width), "Output")
+        if _is_torch(reference) and reference.dim() > 0:
+            r = _Arg(reference, "reference")
+            _same_space(i, r)
+            _expect(r, n, "Reference")
+            _call("fl_for_pack_refs", i.tbits, True, width, n, i.ptr, r.ptr, o.ptr)
+        else:
+            _call("fl_for_pack", i.tbits, dev, width, n, i.ptr, _ref_value(reference, i.tbits), o.ptr)
+
+    @staticmethod
+    def unfor_pack(width: int, input, reference, output) -> None:
+        """`unfor_pack::<W>(input, reference, output)` (:12-17, impl :38-50)."""
+        i, o = _Arg(input, "input"), _Arg(output, "output")
+        dev = _same_space(i, o)
+        _check_width(width, o.tbits)
+        n = _n_blocks_unpacked(o, "Output")
+        _expect(i, n * packed_len(o.tbits, width), "Input")
+        if _is_torch(reference) and reference.dim() > 0:
+            r = _Arg(reference, "reference")
+            _same_space(o, r)
+            _expect(r, n, "Reference")
+            _call("fl_unfor_pack_refs", o.tbits, True, width, n, i.ptr, r.ptr, o.ptr)
+        else:
+            _call("fl_unfor_pack", o.tbits, dev, width, n, i.ptr, _ref_value(reference, o.tbits), o.ptr)
+
+
+class Delta:
+    """src/delta.rs:6-17.  `base` holds LANES = 1024/T elements per block."""
+
+    @staticmethod
+    def _three(input, base, output, packed_width=None):
+        i, b, o = _Arg(input, "input"), _Arg(base, "base"), _Arg(output, "output")
+        dev = _same_space(i, b, o)
+        n = _n_blocks_unpacked(o, "Output")
+        _expect(b, n * (1024 // o.tbits), "Base")
+        if packed_width is None:
+            _expect(i, n * 1024, "Input")
+        else:
+            _check_width(packed_width, o.tbits)
+            _expect(i, n * packed_len(o.tbits, packed_width), "Input")
+        return i, b, o, dev, n
+
+    @staticmethod
+    def delta(input, base, output) -> None:
+        """`delta(input, base, output)` (:7, impl :24-33)."""
+        i, b, o, dev, n = Delta._three(input, base, output)
+        _call("fl_delta", o.tbits, dev, n, i.ptr, b.ptr, o.ptr)
+
+    @staticmethod
+    def undelta(input, base, output) -> None:
+        """`undelta(input, base, output)` (:9, impl :36-45)."""
+        i, b, o, dev, n = Delta._three(input, base, output)
+        _call("fl_undelta", o.tbits, dev, n, i.ptr, b.ptr, o.ptr)
+
+    @staticmethod
+    def undelta_pack(width: int, input, base, output) -> None:
+        """`undelta_pack::<W>(input, base, output)` (:11-17, impl :48-63): fused unpack + prefix-add."""
+        i, b, o, dev, n = Delta._three(input, base, output, packed_width=width)
+        _call("fl_undelta_pack", o.tbits, dev, width, n, i.ptr, b.ptr, o.ptr)
+
+
+class Transpose:
+    """src/transpose.rs:4-7."""
+
+    @staticmethod
+    def _two(input, output):
+        i, o = _Arg(input, "input"), _Arg(output, "output")
+        dev = _same_space(i, o)
+        n = _n_blocks_unpacked(i, "Input")
+        _expect(o, n * 1024, "Output")
+        return i, o, dev, n
+
+    @staticmethod
+    def transpose(input, output) -> None:
+        """`transpose(input, output)`: output[i] = input[transpose(i)] (:5, impl :11-15)."""
+        i, o, dev, n = Transpose._two(input, output)
+        _call("fl_transpose", i.tbits, dev, n, i.ptr, o.ptr)
+
+    @staticmethod
+    def untranspose(input, output) -> None:
+        """`untranspose(input, output)`: output[transpose(i)] = input[i] (:6, impl :18-22)."""
+        i, o, dev, n = Transpose._two(input, output)
+        _call("fl_untranspose", i.tbits, dev, n, i.ptr, o.ptr)
+
+    @staticmethod
+    def transpose_index(idx: int) -> int:
+        """`const fn transpose(idx)` (src/transpose.rs:29-36)."""
+        return (idx % 16) * 64 + FL_ORDER[(idx // 16) % 8] * 8 + idx // 128
+
+
+_lib.lib()  # fail loudly at import time if the CUDA library is missing

@@ -1,0 +1,90 @@
+"""ctypes loader for libfastlanes_b200.so (the C-ABI product library, include/fastlanes_b200.h).
+
+There is no fallback: if the library is missing or does not load, importing the package raises.
+"""
+from __future__ import annotations
+
+import ctypes
+import os
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, "lib", "libfastlanes_b200.so")
+
+FL_OK, FL_ERR_WIDTH, FL_ERR_LEN, FL_ERR_INDEX, FL_ERR_ALIGN, FL_ERR_CUDA, FL_ERR_NULL = range(7)
+
+TYPE_SUFFIXES = {8: "u8", 16: "u16", 32: "u32", 64: "u64"}
+_CT = {8: ctypes.c_uint8, 16: ctypes.c_uint16, 32: ctypes.c_uint32, 64: ctypes.c_uint64}
+
+# name -> (argument kinds) ; 'w' width, 'n' size_t, 'p' pointer, 'r' element by value, 's' stream
+_PER_TYPE = {
+    "fl_pack": "wnpps", "fl_host_pack": "wnpp",
+    "fl_unpack": "wnpps", "fl_host_unpack": "wnpp",
+    "fl_unpack_gather": "wnppnpps", "fl_host_unpack_gather": "wnppnp", "fl_host_unpack_single": "wpnp",
+    "fl_for_pack": "wnprps", "fl_for_pack_refs": "wnppps", "fl_host_for_pack": "wnprp",
+    "fl_unfor_pack": "wnprps", "fl_unfor_pack_refs": "wnppps", "fl_host_unfor_pack": "wnprp",
+    "fl_delta": "nppps".replace(" ", ""), "fl_host_delta": "nppp",
+    "fl_undelta": "nppps", "fl_host_undelta": "nppp",
+    "fl_undelta_pack": "wnppps", "fl_host_undelta_pack": "wnppp",
+    "fl_transpose": "npps", "fl_untranspose": "npps",
+    "fl_host_transpose": "npp", "fl_host_untranspose": "npp",
+}
+_GLOBAL = ["fl_version", "fl_last_error_string", "fl_status_string", "fl_device_count", "fl_host_configure",
+           "fl_host_alloc", "fl_host_free", "fl_host_register", "fl_host_unregister", "fl_shutdown"]
+
+
+def exported_symbols() -> list[str]:
+    """Every symbol include/fastlanes_b200.h declares."""
+    names = list(_GLOBAL)
+    for base in _PER_TYPE:
+        names += [f"{base}_{sfx}" for sfx in TYPE_SUFFIXES.values()]
+    return names
+
+
+class FastLanesError(RuntimeError):
+    """Raised where the reference panics (width > T, index >= 1024, wrong lengths) or CUDA fails."""
+
+    def __init__(self, status: int, message: str):
+        super().__init__(message)
+        self.status = status
+
+
+_lib = None
+
+
+def lib() -> ctypes.CDLL:
+    global _lib
+    if _lib is not None:
+        return _lib
+    if not os.path.exists(LIB_PATH):
+        raise ImportError(
+            f"{LIB_PATH} not found: build it with `make lib` (or __graft_entry__.build()). "
+            "fastlanes_b200 has no CPU fallback.")
+    L = ctypes.CDLL(LIB_PATH)
+    for name in ("fl_version", "fl_last_error_string"):
+        getattr(L, name).restype = ctypes.c_char_p
+    L.fl_status_string.restype = ctypes.c_char_p
+    L.fl_status_string.argtypes = [ctypes.c_int]
+    L.fl_device_count.restype = ctypes.c_int
+    L.fl_host_configure.argtypes = [ctypes.c_size_t, ctypes.c_int]
+    L.fl_host_alloc.argtypes = [ctypes.POINTER(ctypes.c_void_p), ctypes.c_size_t]
+    L.fl_host_free.argtypes = [ctypes.c_void_p]
+    L.fl_host_register.argtypes = [ctypes.c_void_p, ctypes.c_size_t]
+    L.fl_host_unregister.argtypes = [ctypes.c_void_p]
+    for base, kinds in _PER_TYPE.items():
+        for tb, sfx in TYPE_SUFFIXES.items():
+            fn = getattr(L, f"{base}_{sfx}")
+            fn.restype = ctypes.c_int
+            fn.argtypes = [{"w": ctypes.c_uint, "n": ctypes.c_size_t, "p": ctypes.c_void_p, "r": _CT[tb],
+                            "s": ctypes.c_void_p}[k] for k in kinds]
+    _lib = L
+    return L
+
+
+def check(status: int) -> None:
+    if status != FL_OK:
+        L = lib()
+        raise FastLanesError(status, f"{L.fl_status_string(status).decode()}: {L.fl_last_error_string().decode()}")
+
+
+def fn(base: str, tbits: int):
+    return getattr(lib(), f"{base}_{TYPE_SUFFIXES[tbits]}")

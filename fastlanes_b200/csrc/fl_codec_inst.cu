@@ -1,0 +1,83 @@
+// fl_codec_inst.cu — instantiates the width-templated kernels for ONE element type and ONE part
+// (compile with -DFLB_TBITS=8|16|32|64 -DFLB_PART=0|1|2: 0 = unpack family, 1 = pack family, 2 = delta)
+// and builds the runtime-width dispatch tables: the `match width { W => ::<W>() }` of
+// src/bitpacking.rs:82-95, :115-128 in the reference.
+#include "fl_internal.h"
+#include "fl_kernels.cuh"
+
+namespace flb {
+
+#if FLB_TBITS == 8
+using elem_t = uint8_t;
+#elif FLB_TBITS == 16
+using elem_t = uint16_t;
+#elif FLB_TBITS == 32
+using elem_t = uint32_t;
+#elif FLB_TBITS == 64
+using elem_t = uint64_t;
+#else
+#error "FLB_TBITS must be 8/16/32/64"
+#endif
+
+using launch_fn = cudaError_t (*)(const LaunchArgs&);
+
+static inline unsigned grid_for(size_t n_blocks) {
+    return unsigned((n_blocks * kSlicesPerBlock + kThreads - 1) / kThreads);
+}
+
+#if FLB_PART == 0
+template <class T, int W, int OP>
+static cudaError_t do_unpack(const LaunchArgs& a) {
+    unpack_kernel<T, W, OP><<<grid_for(a.n_blocks), kThreads, 0, a.stream>>>(
+        static_cast<const char*>(a.in), static_cast<char*>(a.out), a.n_blocks, static_cast<const T*>(a.refs),
+        T(a.ref_scalar), static_cast<const char*>(a.base));
+    return cudaGetLastError();
+}
+template <class T, int OP, int... W>
+static constexpr std::array<launch_fn, sizeof...(W)> unpack_table(std::integer_sequence<int, W...>) {
+    return {{&do_unpack<T, W, OP>...}};
+}
+template <>
+cudaError_t launch_unpack<elem_t>(int op, const LaunchArgs& a) {
+    using seq = std::make_integer_sequence<int, Lay<elem_t>::TB + 1>;
+    static constexpr auto plain = unpack_table<elem_t, UOP_PLAIN>(seq{});
+    static constexpr auto ffor = unpack_table<elem_t, UOP_FOR>(seq{});
+    static constexpr auto delta = unpack_table<elem_t, UOP_DELTA>(seq{});
+    switch (op) {
+        case kUnpackPlain: return plain[a.width](a);
+        case kUnpackFor: return ffor[a.width](a);
+        default: return delta[a.width](a);
+    }
+}
+#elif FLB_PART == 1
+template <class T, int W, int OP>
+static cudaError_t do_pack(const LaunchArgs& a) {
+    pack_kernel<T, W, OP><<<grid_for(a.n_blocks), kThreads, 0, a.stream>>>(
+        static_cast<const char*>(a.in), static_cast<char*>(a.out), a.n_blocks, static_cast<const T*>(a.refs),
+        T(a.ref_scalar));
+    return cudaGetLastError();
+}
+template <class T, int OP, int... W>
+static constexpr std::array<launch_fn, sizeof...(W)> pack_table(std::integer_sequence<int, W...>) {
+    return {{&do_pack<T, W, OP>...}};
+}
+template <>
+cudaError_t launch_pack<elem_t>(int op, const LaunchArgs& a) {
+    using seq = std::make_integer_sequence<int, Lay<elem_t>::TB + 1>;
+    static constexpr auto plain = pack_table<elem_t, POP_PLAIN>(seq{});
+    static constexpr auto ffor = pack_table<elem_t, POP_FOR>(seq{});
+    return (op == kPackPlain ? plain : ffor)[a.width](a);
+}
+#else
+template <>
+cudaError_t launch_delta<elem_t>(bool undo, const LaunchArgs& a) {
+    const char* in = static_cast<const char*>(a.in);
+    const char* base = static_cast<const char*>(a.base);
+    char* out = static_cast<char*>(a.out);
+    if (undo) delta_kernel<elem_t, true><<<grid_for(a.n_blocks), kThreads, 0, a.stream>>>(in, base, out, a.n_blocks);
+    else delta_kernel<elem_t, false><<<grid_for(a.n_blocks), kThreads, 0, a.stream>>>(in, base, out, a.n_blocks);
+    return cudaGetLastError();
+}
+#endif
+
+}  // namespace flb

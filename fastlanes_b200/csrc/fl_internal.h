@@ -1,0 +1,35 @@
+// fl_internal.h — internal launch interface between the per-type kernel translation units and the C ABI.
+#pragma once
+#include <cstddef>
+#include <cstdint>
+#include <cuda_runtime.h>
+
+namespace flb {
+
+struct LaunchArgs {
+    const void* in = nullptr;    // unpacked input (pack/delta/transpose) or packed input (unpack family)
+    void* out = nullptr;
+    const void* base = nullptr;  // n_blocks x LANES (delta family)
+    const void* refs = nullptr;  // per-block references (FoR family) or nullptr
+    uint64_t ref_scalar = 0;     // used when refs == nullptr
+    size_t n_blocks = 0;
+    unsigned width = 0;
+    cudaStream_t stream = nullptr;
+};
+
+// op codes of launch_unpack / launch_pack (match UnpackOp / PackOp in fl_kernels.cuh)
+enum : int { kUnpackPlain = 0, kUnpackFor = 1, kUnpackDelta = 2 };
+enum : int { kPackPlain = 0, kPackFor = 1 };
+
+// Defined once per element type in fl_codec_inst.cu (compiled with -DFLB_TBITS=8/16/32/64).
+template <class T> cudaError_t launch_unpack(int op, const LaunchArgs& a);
+template <class T> cudaError_t launch_pack(int op, const LaunchArgs& a);
+template <class T> cudaError_t launch_delta(bool undo, const LaunchArgs& a);
+
+// Defined for all types in fl_misc.cu.
+template <class T> cudaError_t launch_transpose(bool undo, const LaunchArgs& a);
+template <class T>
+cudaError_t launch_gather(unsigned width, size_t n_blocks, const T* packed, const uint64_t* global_index, size_t n,
+                          T* out, int* oob_flag, cudaStream_t stream);
+
+}  // namespace flb

@@ -1,0 +1,155 @@
+// fl_misc.cu — transpose / untranspose (a14) and batched unpack_single (a11/a12) kernels, all types.
+#include "fl_device.cuh"
+#include "fl_internal.h"
+
+namespace flb {
+
+// ---------------------------------------------------------------------------------------------------
+// Transpose::transpose / untranspose (src/transpose.rs:11-22).
+//   transposed[i] = original[t(i)],  t(i) = (i%16)*64 + FL_ORDER[(i/16)%8]*8 + i/128   (:29-36)
+// Writing i = a + 16 b + 128 c and o = t(i) = 64 a + 8 FL_ORDER[b] + c the permutation is the axis
+// reversal [a:16][f:8][c:8] -> [c:8][b:8][a:16] with b = FL_ORDER[f] (FL_ORDER is an involution,
+// src/lib.rs:53-59).  One CTA stages kTrBlocks blocks in shared memory with coalesced 16-byte global
+// accesses on both sides; the gather (transpose) / scatter (untranspose) happens on shared memory at
+// element granularity.  Shared rows of 64 originals are padded by one 16-byte unit to spread banks.
+// ---------------------------------------------------------------------------------------------------
+constexpr int kTrThreads = 256;
+
+template <class T>
+struct TrCfg {
+    static constexpr int EPC = 16 / int(sizeof(T));        // elements per 16-byte chunk
+    static constexpr int CHUNKS = 1024 / EPC;               // 16-byte chunks per block
+    static constexpr int ROW_ELEMS = 64 + EPC;              // padded shared row (64 originals + 1 chunk)
+    static constexpr int SMEM_ELEMS = 16 * ROW_ELEMS;       // per block
+    static constexpr int BLOCKS_PER_CTA = (sizeof(T) == 8) ? 2 : (sizeof(T) == 4 ? 4 : 8);
+};
+
+__device__ __forceinline__ int transpose_index(int i) {
+    return (i % 16) * 64 + fl_order((i / 16) % 8) * 8 + i / 128;  // transpose.rs:31-35
+}
+// position of original element o inside the padded shared tile
+template <class T>
+__device__ __forceinline__ int smem_pos(int o) {
+    return (o >> 6) * TrCfg<T>::ROW_ELEMS + (o & 63);
+}
+
+template <class T, bool UNDO>
+__global__ void __launch_bounds__(kTrThreads)
+transpose_kernel(const T* __restrict__ in, T* __restrict__ out, size_t n_blocks) {
+    using C = TrCfg<T>;
+    __shared__ __align__(16) T tile[C::BLOCKS_PER_CTA][C::SMEM_ELEMS];
+    const size_t blk0 = size_t(blockIdx.x) * C::BLOCKS_PER_CTA;
+    const int nb = int(min(size_t(C::BLOCKS_PER_CTA), n_blocks - blk0));
+
+    // Phase 1: coalesced 16-byte loads.  The tile always holds the ORIGINAL-order side:
+    //   transpose:   tile[o] = in[o]          (linear fill)
+    //   untranspose: tile[t(i)] = in[i]       (element scatter while filling)
+    for (int c = threadIdx.x; c < nb * C::CHUNKS; c += kTrThreads) {
+        const int b = c / C::CHUNKS, q = c % C::CHUNKS;
+        const uint4 v = ldg128_stream(reinterpret_cast<const char*>(in + (blk0 + b) * 1024) + q * 16);
+        alignas(16) T e[C::EPC];
+        *reinterpret_cast<uint4*>(e) = v;
+        if constexpr (!UNDO) {
+            // 64 % EPC == 0, so a chunk never crosses a padded row: one 16-byte shared store
+            *reinterpret_cast<uint4*>(&tile[b][smem_pos<T>(q * C::EPC)]) = v;
+        } else {
+#pragma unroll
+            for (int k = 0; k < C::EPC; ++k) tile[b][smem_pos<T>(transpose_index(q * C::EPC + k))] = e[k];
+        }
+    }
+    __syncthreads();
+    // Phase 2: coalesced 16-byte stores.
+    //   transpose:   out[i] = tile[t(i)]      (element gather)
+    //   untranspose: out[o] = tile[o]         (linear drain)
+    for (int c = threadIdx.x; c < nb * C::CHUNKS; c += kTrThreads) {
+        const int b = c / C::CHUNKS, q = c % C::CHUNKS;
+        uint4 v;
+        if constexpr (!UNDO) {
+            alignas(16) T e[C::EPC];
+#pragma unroll
+            for (int k = 0; k < C::EPC; ++k) e[k] = tile[b][smem_pos<T>(transpose_index(q * C::EPC + k))];
+            v = *reinterpret_cast<uint4*>(e);
+        } else {
+            v = *reinterpret_cast<const uint4*>(&tile[b][smem_pos<T>(q * C::EPC)]);
+        }
+        stg128_stream(reinterpret_cast<char*>(out + (blk0 + b) * 1024) + q * 16, v);
+    }
+}
+
+template <class T>
+cudaError_t launch_transpose(bool undo, const LaunchArgs& a) {
+    using C = TrCfg<T>;
+    const unsigned grid = unsigned((a.n_blocks + C::BLOCKS_PER_CTA - 1) / C::BLOCKS_PER_CTA);
+    const T* in = static_cast<const T*>(a.in);
+    T* out = static_cast<T*>(a.out);
+    if (undo) transpose_kernel<T, true><<<grid, kTrThreads, 0, a.stream>>>(in, out, a.n_blocks);
+    else transpose_kernel<T, false><<<grid, kTrThreads, 0, a.stream>>>(in, out, a.n_blocks);
+    return cudaGetLastError();
+}
+
+// ---------------------------------------------------------------------------------------------------
+// Batched BitPacking::unpack_single (src/bitpacking.rs:132-179): one thread per query, runtime width.
+// (lane,row) follow lanes_by_index / rows_by_index (:207-232) in closed form instead of the 1 KiB tables.
+// ---------------------------------------------------------------------------------------------------
+template <class T>
+__global__ void __launch_bounds__(256)
+gather_kernel(unsigned W, size_t n_blocks, const T* __restrict__ packed, const uint64_t* __restrict__ gidx, size_t n,
+              T* __restrict__ out, int* __restrict__ oob_flag) {
+    constexpr unsigned TB = Lay<T>::TB;
+    constexpr unsigned L = Lay<T>::L;
+    const size_t i = size_t(blockIdx.x) * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    const uint64_t g = gidx[i];
+    const uint64_t blk = g >> 10;
+    if (blk >= n_blocks) {  // the reference's assert!(index < 1024) generalised to the batch (:152)
+        out[i] = 0;
+        if (oob_flag) *oob_flag = 1;
+        return;
+    }
+    if (W == 0) {  // :137-140
+        out[i] = 0;
+        return;
+    }
+    const unsigned index = unsigned(g & 1023);
+    const unsigned lane = index % L;                       // :210
+    const unsigned s = index / 128;                        // :225
+    const unsigned f = (index - s * 128 - lane) / 16;      // :226
+    const unsigned row = unsigned(fl_order(int(f))) * 8 + s;  // :227-229
+    const T* p = packed + blk * (size_t(1024) * W / TB);
+    if (W == TB) {  // :159-162
+        out[i] = __ldg(p + L * row + lane);
+        return;
+    }
+    const T mask = T((T(1) << W) - 1);          // :164
+    const unsigned start_bit = row * W;          // :165
+    const unsigned start_word = start_bit / TB;  // :166
+    const unsigned lo_shift = start_bit % TB;    // :167
+    const unsigned remaining = TB - lo_shift;    // :168
+    const T lo = T(__ldg(p + L * start_word + lane) >> lo_shift);  // :170
+    if (remaining >= W) {
+        out[i] = T(lo & mask);  // :171-173
+    } else {
+        const T hi = T(__ldg(p + L * (start_word + 1) + lane) << remaining);  // :176
+        out[i] = T(T(lo | hi) & mask);                                        // :177
+    }
+}
+
+template <class T>
+cudaError_t launch_gather(unsigned width, size_t n_blocks, const T* packed, const uint64_t* global_index, size_t n,
+                          T* out, int* oob_flag, cudaStream_t stream) {
+    if (n == 0) return cudaSuccess;
+    const unsigned grid = unsigned((n + 255) / 256);
+    gather_kernel<T><<<grid, 256, 0, stream>>>(width, n_blocks, packed, global_index, n, out, oob_flag);
+    return cudaGetLastError();
+}
+
+#define FLB_INST(T)                                                                                          \
+    template cudaError_t launch_transpose<T>(bool, const LaunchArgs&);                                       \
+    template cudaError_t launch_gather<T>(unsigned, size_t, const T*, const uint64_t*, size_t, T*, int*,     \
+                                          cudaStream_t);
+FLB_INST(uint8_t)
+FLB_INST(uint16_t)
+FLB_INST(uint32_t)
+FLB_INST(uint64_t)
+
+}  // namespace flb

@@ -1,0 +1,121 @@
+/* fastlanes_b200.h — C ABI of the B200-native FastLanes codec (libfastlanes_b200.so).
+ *
+ * Drop-in boundary for the hot path of spiraldb/fastlanes v0.1.8: the BitPacking / FoR / Delta /
+ * Transpose trait surface over 1024-element blocks of u8/u16/u32/u64 at every bit width.  The
+ * reference has no FFI of its own; each entry point below replaces one trait method
+ * and cites it (paths relative to the reference repo).  INTEGRATION.md shows the Rust `extern "C"`
+ * binding + trait impls a maintainer would add; bindings/rust/ ships them as source.
+ *
+ * Conventions
+ *   - Blocks are contiguous:  unpacked block b = 1024 elements at p + b*1024;
+ *     packed block b = 1024*width/T elements (exactly 128*width bytes, no padding — wire format)
+ *     at p + b*(1024*width/T);  base block b = LANES = 1024/T elements (128 bytes) at base + b*LANES.
+ *   - `width` is the runtime bit width of the `unchecked_*` family (src/bitpacking.rs:30,44,58).
+ *     width > T returns FL_ERR_WIDTH (the reference's unreachable!(), src/bitpacking.rs:93,126,197).
+ *   - Two families per operation:
+ *       fl_<op>_<T>        DEVICE pointers, stream-ordered, asynchronous (`stream` is a cudaStream_t
+ *                          passed as void*; NULL = the legacy default stream).  Pointers must be
+ *                          16-byte aligned (cudaMalloc gives 256) else FL_ERR_ALIGN.  Nothing is
+ *                          allocated, nothing is retained after the stream reaches the call.
+ *       fl_host_<op>_<T>   HOST pointers, synchronous: H2D copy, kernels, D2H copy, chunked and
+ *                          pipelined over internal streams on the current CUDA device.  With
+ *                          n_blocks = 1 these are the reference's single-block trait calls.
+ *                          Page-locked buffers (fl_host_alloc / fl_host_register) copy faster.
+ *   - Input and output must not overlap (Rust's & / &mut guarantee in the reference).
+ *   - No entry point unwinds, aborts or falls back to the CPU: without a usable CUDA device every
+ *     call returns FL_ERR_CUDA.  Thread-safe; fl_last_error_string() is thread-local.
+ */
+#ifndef FASTLANES_B200_H
+#define FASTLANES_B200_H
+#include <stddef.h>
+#include <stdint.h>
+
+#if defined(__GNUC__)
+#define FL_API __attribute__((visibility("default")))
+#else
+#define FL_API
+#endif
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef int fl_status;
+enum {
+    FL_OK = 0,
+    FL_ERR_WIDTH = 1, /* width > T            (src/bitpacking.rs:93,126,197 unreachable!) */
+    FL_ERR_LEN = 2,   /* size overflow        (src/bitpacking.rs:78-80,111-113 debug_assert) */
+    FL_ERR_INDEX = 3, /* index out of range   (src/bitpacking.rs:152 assert!) */
+    FL_ERR_ALIGN = 4, /* device pointer not 16-byte aligned */
+    FL_ERR_CUDA = 5,  /* CUDA runtime error or no device; see fl_last_error_string() */
+    FL_ERR_NULL = 6   /* required pointer is NULL */
+};
+
+/* Library / context -------------------------------------------------------------------------- */
+FL_API const char* fl_version(void);
+FL_API const char* fl_last_error_string(void);       /* thread-local, never NULL */
+FL_API const char* fl_status_string(fl_status s);
+FL_API int fl_device_count(void);                    /* 0 when no usable CUDA device */
+/* Host-path tuning for the CURRENT device: blocks per pipelined chunk (0 = default 16384) and
+ * number of internal streams (0 = default 3).  Takes effect on the next fl_host_* call. */
+FL_API fl_status fl_host_configure(size_t chunk_blocks, int n_streams);
+/* Page-locked host memory helpers (cudaHostAlloc / cudaHostRegister). */
+FL_API fl_status fl_host_alloc(void** p, size_t bytes);
+FL_API fl_status fl_host_free(void* p);
+FL_API fl_status fl_host_register(void* p, size_t bytes);
+FL_API fl_status fl_host_unregister(void* p);
+/* Release the internal streams and staging buffers of every device used by fl_host_* calls. */
+FL_API fl_status fl_shutdown(void);
+
+/* Per-type entry points ------------------------------------------------------------------------ */
+#define FL_DECLARE_TYPE(SFX, T)                                                                                     \
+    /* BitPacking::pack / unchecked_pack — src/bitpacking.rs:19,30 (impl :65-96) */                                 \
+    FL_API fl_status fl_pack_##SFX(unsigned width, size_t n_blocks, const T* in, T* packed, void* stream);                 \
+    FL_API fl_status fl_host_pack_##SFX(unsigned width, size_t n_blocks, const T* in, T* packed);                          \
+    /* BitPacking::unpack / unchecked_unpack — src/bitpacking.rs:33,44 (impl :98-129) */                            \
+    FL_API fl_status fl_unpack_##SFX(unsigned width, size_t n_blocks, const T* packed, T* out, void* stream);              \
+    FL_API fl_status fl_host_unpack_##SFX(unsigned width, size_t n_blocks, const T* packed, T* out);                       \
+    /* BitPacking::unpack_single / unchecked_unpack_single — src/bitpacking.rs:47,58 (impl :132-200),               \
+     * batched: global_index[i] = block*1024 + index_in_block; any index >= n_blocks*1024 -> FL_ERR_INDEX           \
+     * is reported by the host variant; the device variant writes 0 for it and sets *oob_flag (may be NULL). */      \
+    FL_API fl_status fl_unpack_gather_##SFX(unsigned width, size_t n_blocks, const T* packed,                              \
+                                     const uint64_t* global_index, size_t n, T* out, int* oob_flag, void* stream);  \
+    FL_API fl_status fl_host_unpack_gather_##SFX(unsigned width, size_t n_blocks, const T* packed,                         \
+                                          const uint64_t* global_index, size_t n, T* out);                          \
+    FL_API fl_status fl_host_unpack_single_##SFX(unsigned width, const T* packed, size_t index, T* value);                 \
+    /* FoR::for_pack — src/ffor.rs:5-10 (impl :24-36).  `_refs`: one reference per block. */                        \
+    FL_API fl_status fl_for_pack_##SFX(unsigned width, size_t n_blocks, const T* in, T reference, T* packed, void* stream); \
+    FL_API fl_status fl_for_pack_refs_##SFX(unsigned width, size_t n_blocks, const T* in, const T* refs, T* packed,        \
+                                     void* stream);                                                                 \
+    FL_API fl_status fl_host_for_pack_##SFX(unsigned width, size_t n_blocks, const T* in, T reference, T* packed);         \
+    /* FoR::unfor_pack — src/ffor.rs:12-17 (impl :38-50) */                                                         \
+    FL_API fl_status fl_unfor_pack_##SFX(unsigned width, size_t n_blocks, const T* packed, T reference, T* out,            \
+                                  void* stream);                                                                    \
+    FL_API fl_status fl_unfor_pack_refs_##SFX(unsigned width, size_t n_blocks, const T* packed, const T* refs, T* out,     \
+                                       void* stream);                                                               \
+    FL_API fl_status fl_host_unfor_pack_##SFX(unsigned width, size_t n_blocks, const T* packed, T reference, T* out);      \
+    /* Delta::delta — src/delta.rs:7 (impl :24-33); base: n_blocks x LANES */                                       \
+    FL_API fl_status fl_delta_##SFX(size_t n_blocks, const T* in, const T* base, T* out, void* stream);                    \
+    FL_API fl_status fl_host_delta_##SFX(size_t n_blocks, const T* in, const T* base, T* out);                             \
+    /* Delta::undelta — src/delta.rs:9 (impl :36-45) */                                                             \
+    FL_API fl_status fl_undelta_##SFX(size_t n_blocks, const T* in, const T* base, T* out, void* stream);                  \
+    FL_API fl_status fl_host_undelta_##SFX(size_t n_blocks, const T* in, const T* base, T* out);                           \
+    /* Delta::undelta_pack — src/delta.rs:11-17 (impl :48-63): fused unpack + prefix-add */                         \
+    FL_API fl_status fl_undelta_pack_##SFX(unsigned width, size_t n_blocks, const T* packed, const T* base, T* out,        \
+                                    void* stream);                                                                  \
+    FL_API fl_status fl_host_undelta_pack_##SFX(unsigned width, size_t n_blocks, const T* packed, const T* base, T* out);  \
+    /* Transpose::transpose / untranspose — src/transpose.rs:5-6 (impl :11-22) */                                   \
+    FL_API fl_status fl_transpose_##SFX(size_t n_blocks, const T* in, T* out, void* stream);                               \
+    FL_API fl_status fl_untranspose_##SFX(size_t n_blocks, const T* in, T* out, void* stream);                             \
+    FL_API fl_status fl_host_transpose_##SFX(size_t n_blocks, const T* in, T* out);                                        \
+    FL_API fl_status fl_host_untranspose_##SFX(size_t n_blocks, const T* in, T* out);
+
+FL_DECLARE_TYPE(u8, uint8_t)
+FL_DECLARE_TYPE(u16, uint16_t)
+FL_DECLARE_TYPE(u32, uint32_t)
+FL_DECLARE_TYPE(u64, uint64_t)
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* FASTLANES_B200_H */
