@@ -1,0 +1,378 @@
+#!/usr/bin/env python
+"""bench.py — BASELINE.json's metric on BASELINE.json's config, one JSON line on stdout (rank 0).
+
+Workload (configs[1]): u32 `BitPacking::unpack`, width sweep W = 1..32, 2^20 blocks (2^30 values) per
+width per GPU.  One "step" = the 32 kernel launches of the sweep over device-resident packed input
+(uniform-random bits generated on the device: every bit pattern is a valid packing of uniform-random
+W-bit values) into a 4 GiB output buffer.  Every launch streams >= 4.1 GiB, far beyond the 126 MB L2.
+
+  value      whole-job billion ints/s over N GPUs, inputs resident in HBM (CUDA events, max over ranks)
+  e2e        the same sweep through the host-buffer C-ABI call fl_host_unpack_u32 (pinned host
+             buffers; H2D + kernels + D2H inside the timed region)
+  roofline   algorithmic bytes / event-timed kernel duration vs the measured HBM peak
+  cpu_baseline  the CPU oracle (C++ restatement of the reference loops) on the box's host cores,
+             on a bounded sample of the same sweep
+
+`--impl reference` times the reference's CPU path instead (the crate cannot be built here: no Rust
+toolchain, so it is the oracle port — see DESIGN.md) on all host threads.
+
+Multi-GPU (torchrun, one rank per GPU): blocks are independent, so every rank runs the same sweep
+on its own shard with no data-path collective (weak scaling); NCCL carries only the barrier and the
+max-over-ranks reduction of the timings.
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import statistics
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+T_BITS = 32
+WIDTHS = list(range(1, 33))
+FALLBACK_HBM_GBS = 6650.0  # /opt/skills/guides/B200_PROFILING.md fallback when MEASURED_PEAKS.json is absent
+
+
+def algorithmic_bytes_per_block(width: int) -> int:
+    """unpack: 128*W bytes read + 128*T bytes written."""
+    return 128 * (width + T_BITS)
+
+
+def load_peak():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        try:
+            d = json.load(open(p))
+            for k in ("hbm_gbs", "hbm_gb_s", "hbm_GBps"):
+                if k in d:
+                    return float(d[k]), "measured (MEASURED_PEAKS.json hbm_gbs)"
+        except Exception:
+            pass
+    return FALLBACK_HBM_GBS, "fallback 6.65 TB/s (B200_PROFILING.md; MEASURED_PEAKS.json absent)"
+
+
+class ClockSampler:
+    """Samples nvidia-smi clocks / throttle reasons for one GPU while the timed region runs."""
+
+    Q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
+         "clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index: int):
+        self.index = index
+        self.proc = None
+        self.lines = []
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(
+                ["nvidia-smi", f"--id={self.index}", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-lms", "100"],
+                stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.thread = threading.Thread(target=self._pump, daemon=True)
+            self.thread.start()
+        except Exception:
+            self.proc = None
+
+    def _pump(self):
+        for line in self.proc.stdout:
+            self.lines.append((time.time(), line.strip()))
+
+    def mark(self):
+        return time.time()
+
+    def stop(self):
+        if self.proc is not None:
+            self.proc.terminate()  # exact PID we started
+            try:
+                self.proc.wait(timeout=5)
+            except Exception:
+                self.proc.kill()
+
+    def summary(self, t0: float, t1: float):
+        sm, mx, reasons = [], [], set()
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for ts, line in self.lines:
+            if ts < t0 - 0.05 or ts > t1 + 0.15:
+                continue
+            f = [x.strip() for x in line.split(",")]
+            if len(f) < 7:
+                continue
+            try:
+                sm.append(float(f[0])); mx.append(float(f[1]))
+            except ValueError:
+                continue
+            for name, v in zip(names, f[3:7]):
+                if v.lower().startswith("active"):
+                    reasons.add(name)
+        if not sm:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": [], "samples": 0}
+        return {"sm_mhz": statistics.median(sm), "sm_max_mhz": max(mx), "reasons": sorted(reasons), "samples": len(sm)}
+
+
+_CPU_BUFS = {}
+
+
+def cpu_sweep(oracle, np, log2_blocks: int, threads: int, repeats: int):
+    """The oracle's unpack over the same width sweep on a bounded sample; returns (best seconds, ints).
+    Buffers are created (and page-touched) once, outside the timed loop."""
+    n = 1 << log2_blocks
+    if log2_blocks not in _CPU_BUFS:
+        rng = np.random.default_rng(42)
+        packed = rng.integers(0, 1 << 32, size=n * 32 * 32, dtype=np.uint32)  # sized for W = 32
+        _CPU_BUFS[log2_blocks] = (packed, np.zeros(n * 1024, dtype=np.uint32))
+    packed, out = _CPU_BUFS[log2_blocks]
+    best = None
+    for _ in range(repeats):
+        t0 = time.perf_counter()
+        for w in WIDTHS:
+            oracle.run_raw(32, oracle.OP_UNPACK, w, n, packed, out, threads=threads)
+        dt = time.perf_counter() - t0
+        best = dt if best is None else min(best, dt)
+    return best, n * 1024 * len(WIDTHS)
+
+
+def run_reference(args):
+    """`--impl reference`: the reference's CPU path (oracle port) on all host threads; rank 0 only."""
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return 0
+    import numpy as np
+
+    from oracle import fl_oracle as oracle
+
+    threads = oracle.hardware_threads()
+    lg = args.cpu_log2_blocks
+    for _ in range(max(1, args.warmup)):
+        cpu_sweep(oracle, np, lg, threads, 1)
+    t0 = time.perf_counter()
+    ints = 0
+    for _ in range(args.steps):
+        dt, n_ints = cpu_sweep(oracle, np, lg, threads, 1)
+        ints += n_ints
+    total = time.perf_counter() - t0
+    gints = ints / total / 1e9
+    sample = f"u32 unpack W=1..32, 2^{lg} blocks per width per step (host memory), {oracle.isa()}"
+    line = {
+        "impl": "reference", "metric": "u32 unpack width sweep throughput", "value": gints, "unit": "Gint/s",
+        "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup, "ms_per_step": total / args.steps * 1e3,
+        "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "u32", "data": "synthetic",
+        "config": {"workload": "configs[1]: u32 unpack, width sweep W=1..32 (bounded sample of the 2^20-block sweep)",
+                   "blocks_per_width": 1 << lg, "widths": "1..32"},
+        "cpu_baseline": {"value": gints, "unit": "Gint/s", "cores": threads, "kind": "port", "sample": sample},
+        "e2e": {"value": gints, "unit": "Gint/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "note": "reference crate is Rust nightly-2024-06-19 (no toolchain in this image): timed the C++ restatement of its loops",
+    }
+    print(json.dumps(line), flush=True)
+    return 0
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=5)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--log2-blocks", type=int, default=20, help="blocks per width per GPU (configs[1]: 20)")
+    ap.add_argument("--e2e-steps", type=int, default=1, help="timed end-to-end (host buffer) steps; 0 disables")
+    ap.add_argument("--cpu-log2-blocks", type=int, default=15, help="CPU baseline sample: blocks per width")
+    ap.add_argument("--no-cpu", action="store_true")
+    args = ap.parse_args()
+    if args.impl == "reference":
+        return run_reference(args)
+
+    import numpy as np
+    import torch
+
+    import fastlanes_b200 as fl
+    from fastlanes_b200 import _lib
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    assert torch.cuda.is_available(), "bench.py needs a CUDA device (no CPU fallback)"
+    torch.cuda.set_device(local_rank)
+    dist = None
+    if world > 1:
+        import torch.distributed as dist
+
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+    dev = torch.device("cuda", local_rank)
+
+    n_blocks = 1 << args.log2_blocks
+    # packed input sized for W = 32 (each width reads its own 128*W*n_blocks-byte prefix); 4 GiB output
+    packed = torch.empty(n_blocks * 32 * 32, dtype=torch.int32, device=dev)
+    gen = torch.Generator(device=dev); gen.manual_seed(42 + rank)
+    chunk = 1 << 26
+    for i in range(0, packed.numel(), chunk):
+        packed[i:i + chunk].random_(-(1 << 31), (1 << 31) - 1, generator=gen)
+    out = torch.empty(n_blocks * 1024, dtype=torch.int32, device=dev)
+    unpack = _lib.fn("fl_unpack", 32)
+    stream = torch.cuda.current_stream()
+    sp = stream.cuda_stream
+
+    def launch(w):
+        st = unpack(w, n_blocks, packed.data_ptr(), out.data_ptr(), sp)
+        if st != 0:
+            _lib.check(st)
+
+    def step():
+        for w in WIDTHS:
+            launch(w)
+
+    def barrier():
+        if dist is not None:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    for _ in range(max(3, args.warmup)):
+        step()
+    barrier()
+
+    sampler = ClockSampler(local_rank)
+    if rank == 0:
+        sampler.start()
+        time.sleep(0.3)
+
+    # ---- timed region: EXACTLY K steps, events on the launching stream ------------------------
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    barrier()
+    t_mark0 = sampler.mark()
+    e0.record(stream)
+    for _ in range(args.steps):
+        step()
+    e1.record(stream)
+    barrier()
+    t_mark1 = sampler.mark()
+    total_ms = e0.elapsed_time(e1)
+    launches = args.steps * len(WIDTHS)
+
+    # ---- per-width kernel durations (roofline), same K, events around each launch ------------
+    per_w_ms = {}
+    for w in WIDTHS:
+        evs = []
+        for _ in range(args.steps):
+            a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            a.record(stream); launch(w); b.record(stream)
+            evs.append((a, b))
+        torch.cuda.synchronize()
+        per_w_ms[w] = statistics.mean(a.elapsed_time(b) for a, b in evs)
+    if rank == 0:
+        time.sleep(0.2)
+        sampler.stop()
+
+    if dist is not None:
+        t = torch.tensor([total_ms], dtype=torch.float64, device=dev)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        total_ms = float(t.item())
+    ints_per_step = world * len(WIDTHS) * n_blocks * 1024
+    value = ints_per_step * args.steps / (total_ms * 1e-3) / 1e9
+    bytes_per_step_rank = sum(algorithmic_bytes_per_block(w) for w in WIDTHS) * n_blocks
+    gbps = world * bytes_per_step_rank * args.steps / (total_ms * 1e-3) / 1e9
+
+    peak, peak_src = load_peak()
+    kern_ms = sum(per_w_ms.values())
+    achieved = bytes_per_step_rank / (kern_ms * 1e-3) / 1e9
+    per_width = {str(w): {"us": round(per_w_ms[w] * 1e3, 1),
+                          "GBps": round(algorithmic_bytes_per_block(w) * n_blocks / (per_w_ms[w] * 1e-3) / 1e9, 1),
+                          "Gints": round(n_blocks * 1024 / (per_w_ms[w] * 1e-3) / 1e9, 1)} for w in WIDTHS}
+    worst = min(WIDTHS, key=lambda w: per_width[str(w)]["GBps"])
+    roofline = {
+        "bound": "hbm", "kernel": "flb::unpack_kernel<uint32_t, W, UOP_PLAIN> (W=1..32, one launch per width)",
+        "achieved": round(achieved, 1), "peak": peak, "unit": "GB/s", "frac": round(achieved / peak, 4),
+        "peak_source": peak_src, "traffic": None,
+        "algorithmic_bytes_per_launch": "128*(W+32) bytes/block * 2^%d blocks" % args.log2_blocks,
+        "min_frac_over_widths": round(per_width[str(worst)]["GBps"] / peak, 4), "min_frac_width": worst,
+        "per_width": per_width,
+    }
+    tr = os.path.join(ROOT, "profiles", "traffic_r01.json")
+    if os.path.exists(tr):
+        try:
+            roofline["traffic"] = json.load(open(tr)).get("dram_bytes_per_launch_w16")
+        except Exception:
+            pass
+
+    # ---- end to end through the host-buffer C-ABI (pinned host memory) ------------------------
+    e2e = None
+    if args.e2e_steps > 0:
+        h_packed = fl.pinned_empty(n_blocks * 32 * 32, np.uint32)
+        h_out = fl.pinned_empty(n_blocks * 1024, np.uint32)
+        # one D2H of the device-generated packed bits gives the host input (outside the timed region)
+        torch.cuda.synchronize()
+        hp_t = torch.from_numpy(h_packed.view(np.int32))
+        hp_t.copy_(packed)
+        host_unpack = _lib.fn("fl_host_unpack", 32)
+
+        def e2e_step():
+            for w in WIDTHS:
+                st = host_unpack(w, n_blocks, h_packed.ctypes.data, h_out.ctypes.data)
+                if st != 0:
+                    _lib.check(st)
+
+        # warm-up: a reduced sweep (allocates the library's staging buffers, touches all pages)
+        for w in (1, 16, 32):
+            _lib.check(host_unpack(w, n_blocks, h_packed.ctypes.data, h_out.ctypes.data))
+        barrier()
+        t0 = time.perf_counter()
+        for _ in range(args.e2e_steps):
+            e2e_step()
+        torch.cuda.synchronize()
+        e2e_s = time.perf_counter() - t0
+        if dist is not None:
+            t = torch.tensor([e2e_s], dtype=torch.float64, device=dev)
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+            e2e_s = float(t.item())
+        e2e = {"value": round(ints_per_step * args.e2e_steps / e2e_s / 1e9, 3), "unit": "Gint/s",
+               "h2d_bytes_per_step": sum(128 * w for w in WIDTHS) * n_blocks,
+               "d2h_bytes_per_step": len(WIDTHS) * n_blocks * 4096,
+               "steps": args.e2e_steps, "ms_per_step": round(e2e_s / args.e2e_steps * 1e3, 1),
+               "api": "fl_host_unpack_u32 (pinned host buffers, chunked 3-stream H2D/kernel/D2H pipeline), per rank",
+               "timing": "host wall clock around the synchronous C-ABI calls (includes PCIe copies), max over ranks"}
+        # last call's result must equal the device result of the same width
+        check = torch.from_numpy(h_out.view(np.int32)[: 1 << 20]).to(dev)
+        launch(32)
+        torch.cuda.synchronize()
+        assert torch.equal(check, out[: 1 << 20]), "e2e host path disagrees with the device path"
+        del h_packed, h_out
+
+    cpu = None
+    if rank == 0 and not args.no_cpu:
+        from oracle import fl_oracle as oracle
+
+        threads = oracle.hardware_threads()
+        cpu_sweep(oracle, np, args.cpu_log2_blocks, threads, 1)
+        dt, ints = cpu_sweep(oracle, np, args.cpu_log2_blocks, threads, 5)
+        dt1, ints1 = cpu_sweep(oracle, np, max(10, args.cpu_log2_blocks - 4), 1, 2)
+        cpu = {"value": round(ints / dt / 1e9, 3), "unit": "Gint/s", "cores": threads, "kind": "port",
+               "sample": f"u32 unpack W=1..32, 2^{args.cpu_log2_blocks} blocks per width (best of 5), host memory, {oracle.isa()}",
+               "single_thread_Gints": round(ints1 / dt1 / 1e9, 3),
+               "note": "C++ restatement of the reference loops (the Rust crate cannot be built here); a reported baseline, not the target"}
+
+    if dist is not None:
+        dist.barrier()
+        dist.destroy_process_group()
+    if rank != 0:
+        return 0
+    clocks = sampler.summary(t_mark0, t_mark1)
+    line = {
+        "metric": "u32 unpack width sweep throughput", "value": round(value, 2), "unit": "Gint/s",
+        "n_gpus": world, "steps": args.steps, "warmup": max(3, args.warmup), "ms_per_step": round(total_ms / args.steps, 3),
+        "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "u32", "data": "synthetic",
+        "gbps": round(gbps, 1),
+        "config": {"workload": "configs[1]: u32 unpack, width sweep W=1..32, 2^%d blocks per width per GPU" % args.log2_blocks,
+                   "blocks_per_width_per_gpu": n_blocks, "widths": "1..32", "parallelism": f"block-sharded x{world}, no data-path collective",
+                   "l2": "every launch streams >= 4.1 GiB (input prefix + 4 GiB output) >> 126 MB L2; no flush needed",
+                   "input": "device-generated uniform-random bits, seed 42+rank"},
+        "gpu_launches": launches, "roofline": roofline, "e2e": e2e, "cpu_baseline": cpu, "clocks": clocks,
+    }
+    print(json.dumps(line), flush=True)
+    return 0
+
+
+if __name__ == "__main__":
+    sys.exit(main())
