@@ -63,3 +63,4 @@ KBFLAGS_pf16 := -DFLB_PREFETCH=16
 KBFLAGS_t128 := -DFLB_THREADS=128
 KBFLAGS_t512 := -DFLB_THREADS=512
 kbench-variants: $(KB)/kb_base $(KB)/kb_st1 $(KB)/kb_st2 $(KB)/kb_ld1 $(KB)/kb_ld3 $(KB)/kb_pf4 $(KB)/kb_pf16 $(KB)/kb_t128 $(KB)/kb_t512
+KBFLAGS_u32 := -DKB_ONLY_U32

@@ -28,7 +28,9 @@ static inline unsigned grid_for(size_t n_blocks) {
 #if FLB_PART == 0
 template <class T, int W, int OP>
 static cudaError_t do_unpack(const LaunchArgs& a) {
-    unpack_kernel<T, W, OP><<<grid_for(a.n_blocks), kThreads, 0, a.stream>>>(
+    // warp-block layout: one warp per 1024-value block (see fl_kernels.cuh)
+    const unsigned grid = unsigned((a.n_blocks * 32 + kThreads - 1) / kThreads);
+    unpack_warp_kernel<T, W, OP><<<grid, kThreads, 0, a.stream>>>(
         static_cast<const char*>(a.in), static_cast<char*>(a.out), a.n_blocks, static_cast<const T*>(a.refs),
         T(a.ref_scalar), static_cast<const char*>(a.base));
     return cudaGetLastError();

@@ -28,6 +28,9 @@ __host__ __device__ constexpr int fl_order(int i) {
     return o[i];
 }
 
+// run-time FL_ORDER lookup without a memory table: nibble i of 0x73516240 is FL_ORDER[i]
+__device__ __forceinline__ int fl_order_rt(int i) { return int((0x73516240u >> (4 * i)) & 7u); }
+
 template <class T>
 struct Lay {
     static constexpr int TB = int(sizeof(T)) * 8;  // src/lib.rs:25

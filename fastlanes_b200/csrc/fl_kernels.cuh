@@ -105,6 +105,150 @@ unpack_kernel(const char* __restrict__ packed, char* __restrict__ out, size_t n_
 }
 
 // ---------------------------------------------------------------------------------------------------
+// unpack family, "warp-block" layout (the fast path; profiles/access_pattern_r01.txt shows why):
+// ONE WARP = ONE BLOCK.  The four 8-thread groups of the warp split the T rows of the block into four runs
+// of RPG = T/4 consecutive rows; thread (g, j) owns the 16-byte column slice j of its group's rows.  Each
+// warp-wide store then writes 4 x 128 B that are contiguous (u32/u64: 512 B; u16: 2 x 256 B) and the
+// whole block is written by T/4 back-to-back store instructions of one warp, which is what the HBM
+// controller wants (row-slice layout: ~5.9 TB/s, this layout: ~6.7 TB/s on the same bytes).
+//
+// A group's rows occupy bits [q*RPG*W, (q+1)*RPG*W) of every lane stream (q = rank of the group in row
+// order).  The group loads the NA(+1) word-rows covering that range and pre-shifts them by the run-time
+// offset sh0 = (q*RPG*W) mod T with one funnel shift per word; after that every shift, mask and register
+// index is a compile-time constant again (same extract_row<> as the row-slice kernel, ROW = local row).
+// The fused delta prefix-add (src/delta.rs:48-63) becomes a per-thread scan over RPG rows plus a 4-group
+// exclusive scan of the run totals through warp shuffles.
+// ---------------------------------------------------------------------------------------------------
+template <class T>
+struct WarpLay {
+    static constexpr int TB = Lay<T>::TB;
+    static constexpr int RPG = TB / 4;  // rows per group
+    // rank (position in row order) of group g.  u32/u64: {0,2,1,3} makes the 4 groups' rows adjacent in memory.
+    __device__ static __forceinline__ int rank_of_group(int g) {
+        if constexpr (sizeof(T) >= 4) return (g == 1) ? 2 : (g == 2 ? 1 : g);
+        else return g;
+    }
+    __device__ static __forceinline__ int group_of_rank(int q) { return rank_of_group(q); }  // involution / identity
+};
+
+// lane-wise funnel shift right by a RUN-TIME amount sh (0 <= sh < T): low T-sh bits from lo>>sh, rest from hi
+template <class T>
+__device__ __forceinline__ typename Lay<T>::R lane_funnel_rt(typename Lay<T>::R lo, typename Lay<T>::R hi, unsigned sh,
+                                                             typename Lay<T>::R mlow) {
+    using R = typename Lay<T>::R;
+    if constexpr (sizeof(T) == 4) {
+        return __funnelshift_r(lo, hi, sh);
+    } else if constexpr (sizeof(T) == 8) {
+        return (lo >> sh) | ((hi << 1) << (63u - sh));
+    } else {
+        constexpr unsigned TBu = Lay<T>::TB;
+        return ((lo >> sh) & mlow) | ((hi << (TBu - sh)) & R(~mlow));
+    }
+}
+
+template <class T, int W, int OP>
+__global__ void __launch_bounds__(kThreads)
+unpack_warp_kernel(const char* __restrict__ packed, char* __restrict__ out, size_t n_blocks,
+                   const T* __restrict__ refs, T ref_scalar, const char* __restrict__ base) {
+    using R = typename Lay<T>::R;
+    using WL = WarpLay<T>;
+    constexpr int TB = Lay<T>::TB;
+    constexpr int RPG = WL::RPG;
+    constexpr int NR = Lay<T>::NR;
+    const size_t blk = (size_t(blockIdx.x) * kThreads + threadIdx.x) >> 5;
+    if (blk >= n_blocks) return;  // warp-uniform
+    const int lane = threadIdx.x & 31;
+    const int g = lane >> 3, j = lane & 7;
+    const int q = WL::rank_of_group(g);
+
+    const char* pk = packed + blk * (size_t(128) * W) + j * 16;
+    char* o = out + blk * (size_t(128) * TB) + j * 16;
+
+    Slice<T> v[RPG];
+    if constexpr (W == 0) {
+#pragma unroll
+        for (int i = 0; i < RPG; ++i) v[i] = slice_zero<T>();
+    } else if constexpr (W == TB) {
+        // macros.rs:126-132: row r is word-row r
+        seq_rows<RPG>([&](auto ic) {
+            constexpr int i = decltype(ic)::value;
+            v[i] = load_slice<T>(pk + (q * RPG + i) * 128);
+        });
+    } else {
+        constexpr bool ALIGNED = (W % 4) == 0;              // then q*RPG*W is a multiple of T for every q
+        constexpr int NA = (RPG * W + TB - 1) / TB;         // word-rows holding the run once aligned
+        constexpr int NL = ALIGNED ? NA : NA + 1;           // word-rows to load
+        const unsigned bit0 = unsigned(q) * (RPG * W);
+        const unsigned k0 = bit0 / TB, sh0 = bit0 % TB;
+        Slice<T> w[NL];
+        seq_rows<NL>([&](auto mc) {
+            constexpr int m = decltype(mc)::value;
+            const unsigned k = (k0 + m < unsigned(W)) ? k0 + m : unsigned(W - 1);  // clamp: never read past the block
+            w[m] = load_slice<T>(pk + k * 128);
+        });
+        Slice<T> a[NA];
+        if constexpr (ALIGNED) {
+#pragma unroll
+            for (int m = 0; m < NA; ++m) a[m] = w[m];
+        } else {
+            R mlow = 0;
+            if constexpr (sizeof(T) == 2) { const uint32_t mm = 0xFFFFu >> sh0; mlow = mm | (mm << 16); }
+            if constexpr (sizeof(T) == 1) { mlow = (0xFFu >> sh0) * 0x01010101u; }
+            seq_rows<NA>([&](auto mc) {
+                constexpr int m = decltype(mc)::value;
+#pragma unroll
+                for (int r = 0; r < NR; ++r) a[m].r[r] = lane_funnel_rt<T>(w[m].r[r], w[m + 1].r[r], sh0, mlow);
+            });
+        }
+        seq_rows<RPG>([&](auto ic) {
+            constexpr int i = decltype(ic)::value;
+            constexpr int idx = (i * W) / TB;
+            constexpr int nxt = (idx + 1 < NA) ? idx + 1 : idx;  // only read when the field straddles
+            v[i] = extract_row<T, W, i>(a[idx], a[nxt]);
+        });
+    }
+
+    if constexpr (OP == UOP_FOR) {
+        const Slice<T> ref = slice_splat<T>(refs ? refs[blk] : ref_scalar);  // ffor.rs:47
+#pragma unroll
+        for (int i = 0; i < RPG; ++i) v[i] = slice_add<T>(v[i], ref);
+    }
+    if constexpr (OP == UOP_DELTA) {
+        // delta.rs:56-60: running wrapping sum along rows per lane, seeded with base[lane]
+#pragma unroll
+        for (int i = 1; i < RPG; ++i) v[i] = slice_add<T>(v[i], v[i - 1]);
+        Slice<T> carry = load_slice<T>(base + blk * 128 + j * 16);
+#pragma unroll
+        for (int qq = 0; qq < 3; ++qq) {  // totals of the runs that precede this one in row order
+            const int src = WL::group_of_rank(qq) * 8 + j;
+#pragma unroll
+            for (int r = 0; r < NR; ++r) {
+                R t;
+                if constexpr (sizeof(R) == 8) t = __shfl_sync(0xffffffffu, (unsigned long long)v[RPG - 1].r[r], src);
+                else t = __shfl_sync(0xffffffffu, v[RPG - 1].r[r], src);
+                if (qq < q) carry.r[r] = lane_add<T>(carry.r[r], t);
+            }
+        }
+#pragma unroll
+        for (int i = 0; i < RPG; ++i) v[i] = slice_add<T>(v[i], carry);
+    }
+    seq_rows<RPG>([&](auto ic) {
+        constexpr int i = decltype(ic)::value;
+        // global row r = q*RPG + i: offset (FL_ORDER[r/8]*16 + (r%8)*128)*sizeof(T)  (macros.rs:20-24)
+        int off;
+        if constexpr (RPG >= 8) {
+            // r/8 = q*(RPG/8) + i/8 ; r%8 = i%8
+            const int oidx = q * (RPG / 8) + i / 8;
+            off = (fl_order_rt(oidx) * 16 + (i % 8) * 128) * int(sizeof(T));
+        } else {
+            const int r = q * RPG + i;
+            off = (fl_order_rt(r >> 3) * 16 + (r & 7) * 128) * int(sizeof(T));
+        }
+        store_slice<T>(o + off, v[i]);
+    });
+}
+
+// ---------------------------------------------------------------------------------------------------
 // pack family:  a7 BitPacking::pack (src/bitpacking.rs:65-74), a18 FoR::for_pack (src/ffor.rs:24-36).
 //   in : n_blocks x (128*T bytes)        packed : n_blocks x (128*W bytes)
 // ---------------------------------------------------------------------------------------------------

@@ -2,6 +2,9 @@
 #include "fl_oracle.h"
 
 #include <algorithm>
+#include <condition_variable>
+#include <functional>
+#include <mutex>
 #include <thread>
 #include <vector>
 
@@ -50,6 +53,59 @@ const IsaTable& tab() {
     return kTabs[g_level - 2];
 }
 
+// Persistent worker pool: the timed CPU baseline must not pay a thread spawn per call (a 128-thread
+// spawn costs milliseconds, comparable to the work of one width of the bench sample).
+class Pool {
+public:
+    static Pool& get() { static Pool* p = new Pool; return *p; }  // leaked on purpose: workers outlive exit()
+    // run fn(t) for t in [0, n) on n workers (the calling thread takes t = 0)
+    void run(size_t n, const std::function<void(size_t)>& fn) {
+        std::lock_guard<std::mutex> serial(run_mu_);
+        ensure(n - 1);
+        {
+            std::lock_guard<std::mutex> lk(mu_);
+            fn_ = &fn; active_ = n - 1; pending_ = n - 1; ++gen_;
+        }
+        cv_.notify_all();
+        fn(0);
+        std::unique_lock<std::mutex> lk(mu_);
+        done_.wait(lk, [&] { return pending_ == 0; });
+        fn_ = nullptr;
+    }
+private:
+    void ensure(size_t n) {
+        while (workers_.size() < n) {
+            const size_t id = workers_.size();
+            workers_.emplace_back([this, id] { loop(id); });
+            workers_.back().detach();
+        }
+    }
+    void loop(size_t id) {
+        unsigned long seen = 0;
+        for (;;) {
+            const std::function<void(size_t)>* fn;
+            {
+                std::unique_lock<std::mutex> lk(mu_);
+                cv_.wait(lk, [&] { return gen_ != seen; });
+                seen = gen_;
+                if (id >= active_) continue;
+                fn = fn_;
+            }
+            (*fn)(id + 1);
+            {
+                std::lock_guard<std::mutex> lk(mu_);
+                if (--pending_ == 0) done_.notify_one();
+            }
+        }
+    }
+    std::mutex run_mu_, mu_;
+    std::condition_variable cv_, done_;
+    std::vector<std::thread> workers_;
+    const std::function<void(size_t)>* fn_ = nullptr;
+    size_t active_ = 0, pending_ = 0;
+    unsigned long gen_ = 0;
+};
+
 int type_slot(int tbits) {
     switch (tbits) {
         case 8: return 0;
@@ -97,13 +153,10 @@ int flo_run(int tbits, int op, unsigned width, size_t n_blocks, const void* in, 
         return FLO_OK;
     }
     const size_t nt = std::min<size_t>(size_t(n_threads), n_blocks);
-    std::vector<std::thread> th;
-    th.reserve(nt);
-    for (size_t t = 0; t < nt; ++t) {
+    Pool::get().run(nt, [=](size_t t) {
         const size_t b0 = n_blocks * t / nt, b1 = n_blocks * (t + 1) / nt;
-        th.emplace_back([=] { run(op, width, b0, b1, in, out, base, refs, ref_scalar); });
-    }
-    for (auto& t : th) t.join();
+        run(op, width, b0, b1, in, out, base, refs, ref_scalar);
+    });
     return FLO_OK;
 }
 

@@ -86,6 +86,18 @@ static void bench_width(const Ctx& c, const std::string& op) {
     if (op == "unpack") {
         float ms = time_ms(c, [&] { unpack_kernel<T, W, UOP_PLAIN><<<grid, kThreads, 0, c.s>>>(c.in, c.out, c.n_blocks, nullptr, T(0), nullptr); });
         report("unpack", TB, W, c.n_blocks, 128 * (W + TB), ms);
+    } else if (op == "unpackB" || op == "unfor_packB" || op == "undelta_packB") {
+        const unsigned gridB = unsigned((c.n_blocks * 32 + kThreads - 1) / kThreads);
+        if (op == "unpackB") {
+            float ms = time_ms(c, [&] { unpack_warp_kernel<T, W, UOP_PLAIN><<<gridB, kThreads, 0, c.s>>>(c.in, c.out, c.n_blocks, nullptr, T(0), nullptr); });
+            report("unpackB", TB, W, c.n_blocks, 128 * (W + TB), ms);
+        } else if (op == "unfor_packB") {
+            float ms = time_ms(c, [&] { unpack_warp_kernel<T, W, UOP_FOR><<<gridB, kThreads, 0, c.s>>>(c.in, c.out, c.n_blocks, nullptr, T(12345), nullptr); });
+            report("unfor_packB", TB, W, c.n_blocks, 128 * (W + TB), ms);
+        } else {
+            float ms = time_ms(c, [&] { unpack_warp_kernel<T, W, UOP_DELTA><<<gridB, kThreads, 0, c.s>>>(c.in, c.out, c.n_blocks, nullptr, T(0), c.base); });
+            report("undelta_packB", TB, W, c.n_blocks, 128 * (W + TB + 1), ms);
+        }
     } else if (op == "unfor_pack") {
         float ms = time_ms(c, [&] { unpack_kernel<T, W, UOP_FOR><<<grid, kThreads, 0, c.s>>>(c.in, c.out, c.n_blocks, nullptr, T(12345), nullptr); });
         report("unfor_pack", TB, W, c.n_blocks, 128 * (W + TB), ms);
@@ -159,10 +171,12 @@ int main(int argc, char** argv) {
         return 0;
     }
     switch (tb) {
+#ifndef KB_ONLY_U32
         case 8: run_type<uint8_t>(c, op, lo, hi); break;
         case 16: run_type<uint16_t>(c, op, lo, hi); break;
-        case 32: run_type<uint32_t>(c, op, lo, hi); break;
         case 64: run_type<uint64_t>(c, op, lo, hi); break;
+#endif
+        case 32: run_type<uint32_t>(c, op, lo, hi); break;
         default: fprintf(stderr, "bad tbits\n"); return 2;
     }
     return 0;
