@@ -15,7 +15,7 @@ HDRS := $(SRC)/fl_device.cuh $(SRC)/fl_kernels.cuh $(SRC)/fl_internal.h include/
 CODEC_OBJS := $(foreach t,$(TYPES),$(foreach p,$(PARTS),$(OBJ)/codec_u$(t)_p$(p).o))
 OBJS := $(CODEC_OBJS) $(OBJ)/fl_misc.o $(OBJ)/fl_api.o
 
-all: lib oracle
+all: lib oracle build/test_traits
 lib: $(LIB)
 oracle:
 	$(MAKE) -C oracle
@@ -64,3 +64,7 @@ KBFLAGS_t128 := -DFLB_THREADS=128
 KBFLAGS_t512 := -DFLB_THREADS=512
 kbench-variants: $(KB)/kb_base $(KB)/kb_st1 $(KB)/kb_st2 $(KB)/kb_ld1 $(KB)/kb_ld3 $(KB)/kb_pf4 $(KB)/kb_pf16 $(KB)/kb_t128 $(KB)/kb_t512
 KBFLAGS_u32 := -DKB_ONLY_U32
+
+# C++ trait-mirror test binary (run on the GPU box by tests/test_gpu_cpp_traits.py)
+build/test_traits: tests/cpp/test_traits.cpp include/fastlanes_b200.hpp include/fastlanes_b200.h $(LIB)
+	g++ -std=c++17 -O1 -Iinclude -o $@ $< -Lfastlanes_b200/lib -lfastlanes_b200 -Wl,-rpath,'$$ORIGIN/../fastlanes_b200/lib'

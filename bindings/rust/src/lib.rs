@@ -1,0 +1,225 @@
+//! Rust host side of the B200 FastLanes codec: the trait surface of `spiraldb/fastlanes` v0.1.8
+//! (`BitPacking`, `FoR`, `Delta`, `Transpose` for `u8/u16/u32/u64`) implemented over the
+//! `extern "C"` ABI of `libfastlanes_b200.so` (`include/fastlanes_b200.h`).
+//!
+//! NOT COMPILED IN THIS REPOSITORY'S CI: the build image has no Rust toolchain.  The parity of the
+//! C ABI itself is tested from Python (`tests/`); this file is the binding a maintainer adds.
+//!
+//! Two levels:
+//!  * the **trait impls** below are drop-in for the reference's single-block calls (host slices in,
+//!    host slices out; one `fl_host_*` call = H2D copy + sm_100a kernel + D2H copy).  Where the
+//!    reference panics (`unreachable!` on `width > T`, `assert!(index < 1024)`, `debug_assert` on
+//!    slice lengths) these panic too, so behaviour is identical;
+//!  * the **`device` module** exposes the batched, stream-ordered entry points on device pointers,
+//!    which is where the throughput is (a whole column chunk per call, data resident in HBM).
+//!
+//! Unlike the reference, the const-generic `W` forms need no `generic_const_exprs`: the packed
+//! length is checked at run time against `1024 * W / T`.
+#![allow(clippy::missing_safety_doc)]
+
+use core::ffi::c_void;
+
+pub const FL_ORDER: [usize; 8] = [0, 4, 2, 6, 1, 5, 3, 7];
+
+/// Status codes of `include/fastlanes_b200.h`.
+pub mod status {
+    pub const OK: i32 = 0;
+    pub const ERR_WIDTH: i32 = 1;
+    pub const ERR_LEN: i32 = 2;
+    pub const ERR_INDEX: i32 = 3;
+    pub const ERR_ALIGN: i32 = 4;
+    pub const ERR_CUDA: i32 = 5;
+    pub const ERR_NULL: i32 = 6;
+}
+
+extern "C" {
+    fn fl_last_error_string() -> *const core::ffi::c_char;
+}
+
+fn check(st: i32, what: &str) {
+    if st != status::OK {
+        let msg = unsafe { std::ffi::CStr::from_ptr(fl_last_error_string()) }.to_string_lossy().into_owned();
+        match st {
+            status::ERR_WIDTH => unreachable!("Unsupported width ({what}): {msg}"),
+            status::ERR_INDEX => panic!("Index must be less than 1024 ({what}): {msg}"),
+            _ => panic!("fastlanes_b200 {what} failed with status {st}: {msg}"),
+        }
+    }
+}
+
+pub trait FastLanes: Sized + Copy {
+    const T: usize = core::mem::size_of::<Self>() * 8;
+    const LANES: usize = 1024 / Self::T;
+}
+
+pub trait BitPacking: FastLanes {
+    fn pack<const W: usize>(input: &[Self; 1024], output: &mut [Self]);
+    unsafe fn unchecked_pack(width: usize, input: &[Self], output: &mut [Self]);
+    fn unpack<const W: usize>(input: &[Self], output: &mut [Self; 1024]);
+    unsafe fn unchecked_unpack(width: usize, input: &[Self], output: &mut [Self]);
+    fn unpack_single<const W: usize>(packed: &[Self], index: usize) -> Self;
+    unsafe fn unchecked_unpack_single(width: usize, packed: &[Self], index: usize) -> Self;
+}
+
+pub trait FoR: BitPacking {
+    fn for_pack<const W: usize>(input: &[Self; 1024], reference: Self, output: &mut [Self]);
+    fn unfor_pack<const W: usize>(input: &[Self], reference: Self, output: &mut [Self; 1024]);
+}
+
+pub trait Delta: BitPacking {
+    fn delta(input: &[Self; 1024], base: &[Self], output: &mut [Self; 1024]);
+    fn undelta(input: &[Self; 1024], base: &[Self], output: &mut [Self; 1024]);
+    fn undelta_pack<const W: usize>(input: &[Self], base: &[Self], output: &mut [Self; 1024]);
+}
+
+pub trait Transpose: FastLanes {
+    fn transpose(input: &[Self; 1024], output: &mut [Self; 1024]);
+    fn untranspose(input: &[Self; 1024], output: &mut [Self; 1024]);
+}
+
+/// `const fn transpose(idx)` of the reference (src/transpose.rs:29-36).
+pub const fn transpose(idx: usize) -> usize {
+    (idx % 16) * 64 + FL_ORDER[(idx / 16) % 8] * 8 + idx / 128
+}
+
+macro_rules! bind_type {
+    ($T:ty, $pack:ident, $unpack:ident, $single:ident, $for_pack:ident, $unfor_pack:ident,
+     $delta:ident, $undelta:ident, $undelta_pack:ident, $transpose:ident, $untranspose:ident) => {
+        extern "C" {
+            fn $pack(width: u32, n_blocks: usize, input: *const $T, packed: *mut $T) -> i32;
+            fn $unpack(width: u32, n_blocks: usize, packed: *const $T, out: *mut $T) -> i32;
+            fn $single(width: u32, packed: *const $T, index: usize, value: *mut $T) -> i32;
+            fn $for_pack(width: u32, n_blocks: usize, input: *const $T, reference: $T, packed: *mut $T) -> i32;
+            fn $unfor_pack(width: u32, n_blocks: usize, packed: *const $T, reference: $T, out: *mut $T) -> i32;
+            fn $delta(n_blocks: usize, input: *const $T, base: *const $T, out: *mut $T) -> i32;
+            fn $undelta(n_blocks: usize, input: *const $T, base: *const $T, out: *mut $T) -> i32;
+            fn $undelta_pack(width: u32, n_blocks: usize, packed: *const $T, base: *const $T, out: *mut $T) -> i32;
+            fn $transpose(n_blocks: usize, input: *const $T, out: *mut $T) -> i32;
+            fn $untranspose(n_blocks: usize, input: *const $T, out: *mut $T) -> i32;
+        }
+
+        impl FastLanes for $T {}
+
+        impl BitPacking for $T {
+            fn pack<const W: usize>(input: &[Self; 1024], output: &mut [Self]) {
+                assert_eq!(output.len(), 1024 * W / Self::T, "Output buffer must be of size 1024 * W / T");
+                check(unsafe { $pack(W as u32, 1, input.as_ptr(), output.as_mut_ptr()) }, "pack");
+            }
+            unsafe fn unchecked_pack(width: usize, input: &[Self], output: &mut [Self]) {
+                debug_assert_eq!(input.len(), 1024, "Input buffer must be of size 1024");
+                debug_assert_eq!(output.len(), 128 * width / core::mem::size_of::<Self>());
+                check($pack(width as u32, 1, input.as_ptr(), output.as_mut_ptr()), "unchecked_pack");
+            }
+            fn unpack<const W: usize>(input: &[Self], output: &mut [Self; 1024]) {
+                assert_eq!(input.len(), 1024 * W / Self::T, "Input buffer must be of size 1024 * W / T");
+                check(unsafe { $unpack(W as u32, 1, input.as_ptr(), output.as_mut_ptr()) }, "unpack");
+            }
+            unsafe fn unchecked_unpack(width: usize, input: &[Self], output: &mut [Self]) {
+                debug_assert_eq!(output.len(), 1024, "Output buffer must be of size 1024");
+                debug_assert_eq!(input.len(), 128 * width / core::mem::size_of::<Self>());
+                check($unpack(width as u32, 1, input.as_ptr(), output.as_mut_ptr()), "unchecked_unpack");
+            }
+            fn unpack_single<const W: usize>(packed: &[Self], index: usize) -> Self {
+                assert_eq!(packed.len(), 1024 * W / Self::T);
+                let mut v: $T = 0;
+                check(unsafe { $single(W as u32, packed.as_ptr(), index, &mut v) }, "unpack_single");
+                v
+            }
+            unsafe fn unchecked_unpack_single(width: usize, packed: &[Self], index: usize) -> Self {
+                let mut v: $T = 0;
+                check($single(width as u32, packed.as_ptr(), index, &mut v), "unchecked_unpack_single");
+                v
+            }
+        }
+
+        impl FoR for $T {
+            fn for_pack<const W: usize>(input: &[Self; 1024], reference: Self, output: &mut [Self]) {
+                assert_eq!(output.len(), 1024 * W / Self::T);
+                check(unsafe { $for_pack(W as u32, 1, input.as_ptr(), reference, output.as_mut_ptr()) }, "for_pack");
+            }
+            fn unfor_pack<const W: usize>(input: &[Self], reference: Self, output: &mut [Self; 1024]) {
+                assert_eq!(input.len(), 1024 * W / Self::T);
+                check(unsafe { $unfor_pack(W as u32, 1, input.as_ptr(), reference, output.as_mut_ptr()) }, "unfor_pack");
+            }
+        }
+
+        impl Delta for $T {
+            fn delta(input: &[Self; 1024], base: &[Self], output: &mut [Self; 1024]) {
+                assert_eq!(base.len(), Self::LANES);
+                check(unsafe { $delta(1, input.as_ptr(), base.as_ptr(), output.as_mut_ptr()) }, "delta");
+            }
+            fn undelta(input: &[Self; 1024], base: &[Self], output: &mut [Self; 1024]) {
+                assert_eq!(base.len(), Self::LANES);
+                check(unsafe { $undelta(1, input.as_ptr(), base.as_ptr(), output.as_mut_ptr()) }, "undelta");
+            }
+            fn undelta_pack<const W: usize>(input: &[Self], base: &[Self], output: &mut [Self; 1024]) {
+                assert_eq!(input.len(), 1024 * W / Self::T);
+                assert_eq!(base.len(), Self::LANES);
+                check(unsafe { $undelta_pack(W as u32, 1, input.as_ptr(), base.as_ptr(), output.as_mut_ptr()) }, "undelta_pack");
+            }
+        }
+
+        impl Transpose for $T {
+            fn transpose(input: &[Self; 1024], output: &mut [Self; 1024]) {
+                check(unsafe { $transpose(1, input.as_ptr(), output.as_mut_ptr()) }, "transpose");
+            }
+            fn untranspose(input: &[Self; 1024], output: &mut [Self; 1024]) {
+                check(unsafe { $untranspose(1, input.as_ptr(), output.as_mut_ptr()) }, "untranspose");
+            }
+        }
+    };
+}
+
+bind_type!(u8, fl_host_pack_u8, fl_host_unpack_u8, fl_host_unpack_single_u8, fl_host_for_pack_u8, fl_host_unfor_pack_u8,
+           fl_host_delta_u8, fl_host_undelta_u8, fl_host_undelta_pack_u8, fl_host_transpose_u8, fl_host_untranspose_u8);
+bind_type!(u16, fl_host_pack_u16, fl_host_unpack_u16, fl_host_unpack_single_u16, fl_host_for_pack_u16, fl_host_unfor_pack_u16,
+           fl_host_delta_u16, fl_host_undelta_u16, fl_host_undelta_pack_u16, fl_host_transpose_u16, fl_host_untranspose_u16);
+bind_type!(u32, fl_host_pack_u32, fl_host_unpack_u32, fl_host_unpack_single_u32, fl_host_for_pack_u32, fl_host_unfor_pack_u32,
+           fl_host_delta_u32, fl_host_undelta_u32, fl_host_undelta_pack_u32, fl_host_transpose_u32, fl_host_untranspose_u32);
+bind_type!(u64, fl_host_pack_u64, fl_host_unpack_u64, fl_host_unpack_single_u64, fl_host_for_pack_u64, fl_host_unfor_pack_u64,
+           fl_host_delta_u64, fl_host_undelta_u64, fl_host_undelta_pack_u64, fl_host_transpose_u64, fl_host_untranspose_u64);
+
+/// Batched, stream-ordered entry points on DEVICE pointers (the throughput path).
+/// `stream` is a `cudaStream_t`; null = the legacy default stream.  Pointers must be 16-byte aligned.
+pub mod device {
+    use super::c_void;
+    extern "C" {
+        pub fn fl_unpack_u32(width: u32, n_blocks: usize, packed: *const u32, out: *mut u32, stream: *mut c_void) -> i32;
+        pub fn fl_pack_u32(width: u32, n_blocks: usize, input: *const u32, packed: *mut u32, stream: *mut c_void) -> i32;
+        pub fn fl_unfor_pack_u32(width: u32, n_blocks: usize, packed: *const u32, reference: u32, out: *mut u32, stream: *mut c_void) -> i32;
+        pub fn fl_undelta_pack_u32(width: u32, n_blocks: usize, packed: *const u32, base: *const u32, out: *mut u32, stream: *mut c_void) -> i32;
+        pub fn fl_unpack_gather_u32(width: u32, n_blocks: usize, packed: *const u32, global_index: *const u64, n: usize,
+                                    out: *mut u32, oob_flag: *mut i32, stream: *mut c_void) -> i32;
+        // ... the same set exists for u8 / u16 / u64 and for pack / for_pack / delta / undelta / (un)transpose:
+        // see include/fastlanes_b200.h (FL_DECLARE_TYPE).
+    }
+}
+
+#[cfg(test)]
+mod tests {
+    //! The reference's own tests, verbatim in spirit (src/bitpacking.rs:249-271, src/lib.rs:71-96).
+    use super::*;
+
+    #[test]
+    fn pack_u16_into_u3() {
+        const W: usize = 3;
+        let mut values = [0u16; 1024];
+        for i in 0..1024 { values[i] = (i % (1 << W)) as u16; }
+        let mut packed = [0u16; 128 * W / 2];
+        <u16 as BitPacking>::pack::<W>(&values, &mut packed);
+        let mut unpacked = [0u16; 1024];
+        <u16 as BitPacking>::unpack::<W>(&packed, &mut unpacked);
+        assert_eq!(values, unpacked);
+        for i in 0..1024 { assert_eq!(<u16 as BitPacking>::unpack_single::<W>(&packed, i), values[i]); }
+    }
+
+    #[test]
+    fn unchecked_pack_u32_w10() {
+        let input: [u32; 1024] = core::array::from_fn(|i| i as u32);
+        let mut packed = [0u32; 320];
+        unsafe { <u32 as BitPacking>::unchecked_pack(10, &input, &mut packed) };
+        let mut output = [0u32; 1024];
+        unsafe { <u32 as BitPacking>::unchecked_unpack(10, &packed, &mut output) };
+        assert_eq!(input, output);
+    }
+}
