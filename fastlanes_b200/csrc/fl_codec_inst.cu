@@ -54,7 +54,8 @@ cudaError_t launch_unpack<elem_t>(int op, const LaunchArgs& a) {
 #elif FLB_PART == 1
 template <class T, int W, int OP>
 static cudaError_t do_pack(const LaunchArgs& a) {
-    pack_kernel<T, W, OP><<<grid_for(a.n_blocks), kThreads, 0, a.stream>>>(
+    const unsigned grid = unsigned((a.n_blocks * 32 + kThreads - 1) / kThreads);  // warp-block layout
+    pack_warp_kernel<T, W, OP><<<grid, kThreads, 0, a.stream>>>(
         static_cast<const char*>(a.in), static_cast<char*>(a.out), a.n_blocks, static_cast<const T*>(a.refs),
         T(a.ref_scalar));
     return cudaGetLastError();
@@ -76,8 +77,9 @@ cudaError_t launch_delta<elem_t>(bool undo, const LaunchArgs& a) {
     const char* in = static_cast<const char*>(a.in);
     const char* base = static_cast<const char*>(a.base);
     char* out = static_cast<char*>(a.out);
-    if (undo) delta_kernel<elem_t, true><<<grid_for(a.n_blocks), kThreads, 0, a.stream>>>(in, base, out, a.n_blocks);
-    else delta_kernel<elem_t, false><<<grid_for(a.n_blocks), kThreads, 0, a.stream>>>(in, base, out, a.n_blocks);
+    const unsigned grid = unsigned((a.n_blocks * 32 + kThreads - 1) / kThreads);  // warp-block layout
+    if (undo) delta_warp_kernel<elem_t, true><<<grid, kThreads, 0, a.stream>>>(in, base, out, a.n_blocks);
+    else delta_warp_kernel<elem_t, false><<<grid, kThreads, 0, a.stream>>>(in, base, out, a.n_blocks);
     return cudaGetLastError();
 }
 #endif

@@ -248,6 +248,203 @@ unpack_warp_kernel(const char* __restrict__ packed, char* __restrict__ out, size
     });
 }
 
+// byte offset of local row i of the run of rank q (global row r = q*RPG + i), see row_byte_offset()
+template <class T, int I>
+__device__ __forceinline__ int warp_row_offset(int q) {
+    constexpr int RPG = WarpLay<T>::RPG;
+    if constexpr (RPG >= 8) {
+        const int oidx = q * (RPG / 8) + I / 8;  // r/8 ; r%8 = I%8
+        return (fl_order_rt(oidx) * 16 + (I % 8) * 128) * int(sizeof(T));
+    } else {
+        const int r = q * RPG + I;
+        return (fl_order_rt(r >> 3) * 16 + (r & 7) * 128) * int(sizeof(T));
+    }
+}
+
+template <class R>
+__device__ __forceinline__ R shfl_reg(R v, int src) {
+    if constexpr (sizeof(R) == 8) return R(__shfl_sync(0xffffffffu, (unsigned long long)v, src));
+    else return R(__shfl_sync(0xffffffffu, v, src));
+}
+
+// lane-wise funnel shift LEFT by a run-time amount sh (0 <= sh < T): (hi << sh) | (lo >> (T - sh))
+template <class T>
+__device__ __forceinline__ typename Lay<T>::R lane_funnel_left_rt(typename Lay<T>::R lo, typename Lay<T>::R hi, unsigned sh,
+                                                                  typename Lay<T>::R mlow) {
+    using R = typename Lay<T>::R;
+    if constexpr (sizeof(T) == 4) {
+        return __funnelshift_l(lo, hi, sh);
+    } else if constexpr (sizeof(T) == 8) {
+        return (hi << sh) | ((lo >> 1) >> (63u - sh));
+    } else {
+        constexpr unsigned TBu = Lay<T>::TB;
+        return ((hi << sh) & R(~mlow)) | ((lo >> (TBu - sh)) & mlow);  // mlow = low `sh` bits of every lane
+    }
+}
+
+// ---------------------------------------------------------------------------------------------------
+// pack family, warp-block layout: a7 BitPacking::pack (src/bitpacking.rs:65-74), a18 FoR::for_pack
+// (src/ffor.rs:24-36).  Same thread mapping as unpack_warp_kernel.  Each group packs its T/4 rows into an
+// aligned run (compile-time shifts), funnel-shifts the run left by sh0 into stream position, and word-rows
+// that straddle two (or, for W < 4, up to four) groups are OR-merged through warp shuffles: the
+// higher-rank group owns a shared word.
+// ---------------------------------------------------------------------------------------------------
+template <class T, int W, int OP>
+__global__ void __launch_bounds__(kThreads)
+pack_warp_kernel(const char* __restrict__ in, char* __restrict__ packed, size_t n_blocks,
+                 const T* __restrict__ refs, T ref_scalar) {
+    using R = typename Lay<T>::R;
+    using WL = WarpLay<T>;
+    constexpr int TB = Lay<T>::TB;
+    constexpr int RPG = WL::RPG;
+    constexpr int NR = Lay<T>::NR;
+    const size_t blk = (size_t(blockIdx.x) * kThreads + threadIdx.x) >> 5;
+    if (blk >= n_blocks) return;  // warp-uniform
+    if constexpr (W == 0) return;  // macros.rs:52
+    const int lane = threadIdx.x & 31;
+    const int g = lane >> 3, j = lane & 7;
+    const int q = WL::rank_of_group(g);
+    const char* ip = in + blk * (size_t(128) * TB) + j * 16;
+    char* pk = packed + blk * (size_t(128) * W) + j * 16;
+
+    Slice<T> src[RPG];
+    seq_rows<RPG>([&](auto ic) {
+        constexpr int i = decltype(ic)::value;
+        src[i] = load_slice<T>(ip + warp_row_offset<T, i>(q));
+    });
+    if constexpr (OP == POP_FOR) {
+        const Slice<T> ref = slice_splat<T>(refs ? refs[blk] : ref_scalar);  // ffor.rs:33
+#pragma unroll
+        for (int i = 0; i < RPG; ++i) src[i] = slice_sub<T>(src[i], ref);
+    }
+    if constexpr (W == TB) {
+        // macros.rs:54-59: verbatim, word-row = row
+        seq_rows<RPG>([&](auto ic) {
+            constexpr int i = decltype(ic)::value;
+            store_slice<T>(pk + (q * RPG + i) * 128, src[i]);
+        });
+    } else {
+        constexpr int NA = (RPG * W + TB - 1) / TB;
+        constexpr R MW = rep_mask<T>(W);
+        Slice<T> a[NA + 1];
+#pragma unroll
+        for (int m = 0; m <= NA; ++m) a[m] = slice_zero<T>();
+        seq_rows<RPG>([&](auto ic) {
+            constexpr int i = decltype(ic)::value;
+            constexpr int idx = (i * W) / TB;
+            constexpr int sh = (i * W) % TB;
+#pragma unroll
+            for (int r = 0; r < NR; ++r) {
+                const R v = src[i].r[r] & MW;  // macros.rs:73
+                if constexpr (sh + W <= TB) {
+                    a[idx].r[r] |= (sh == 0) ? v : R(v << sh);  // fits the lane: cannot leak (macros.rs:79)
+                } else {
+                    a[idx].r[r] |= lane_shl<T, sh>(v);
+                    a[idx + 1].r[r] |= lane_shr_keep<T, TB - sh, W - (TB - sh)>(v);  // macros.rs:92
+                }
+            }
+        });
+        constexpr bool ALIGNED = (W % 4) == 0;
+        const unsigned bit0 = unsigned(q) * (RPG * W);
+        const unsigned k0 = bit0 / TB;
+        if constexpr (ALIGNED) {
+            seq_rows<NA>([&](auto mc) {
+                constexpr int m = decltype(mc)::value;
+                store_slice<T>(pk + (k0 + m) * 128, a[m]);
+            });
+        } else {
+            const unsigned sh0 = bit0 % TB;
+            R mlow = 0;
+            if constexpr (sizeof(T) == 2) { const uint32_t mm = (1u << sh0) - 1u; mlow = mm | (mm << 16); }
+            if constexpr (sizeof(T) == 1) { mlow = ((1u << sh0) - 1u) * 0x01010101u; }
+            // s[m] = stream word k0+m restricted to this group's bits, m = 0..NA  (a[NA] == 0 by construction)
+            Slice<T> s[NA + 1];
+            seq_rows<NA + 1>([&](auto mc) {
+                constexpr int m = decltype(mc)::value;
+#pragma unroll
+                for (int r = 0; r < NR; ++r) {
+                    const R lo = (m == 0) ? R(0) : a[m > 0 ? m - 1 : 0].r[r];
+                    s[m].r[r] = lane_funnel_left_rt<T>(lo, a[m].r[r], sh0, mlow);
+                }
+            });
+            // d = number of stream words this group owns = index of the word shared with / owned by the next rank
+            const bool full = (sh0 + unsigned(RPG * W)) / TB == unsigned(NA);  // d == NA, else d == NA-1
+#pragma unroll
+            for (int step = 1; step <= 3; ++step) {
+                const int srcl = WL::group_of_rank(step - 1) * 8 + j;
+#pragma unroll
+                for (int r = 0; r < NR; ++r) {
+                    const R mine = full ? s[NA].r[r] : s[NA - 1].r[r];  // s[d]; includes earlier merges when NA == 1
+                    const R c = shfl_reg<R>(mine, srcl);
+                    if (q == step && sh0 != 0) s[0].r[r] |= c;
+                }
+            }
+            seq_rows<NA>([&](auto mc) {
+                constexpr int m = decltype(mc)::value;
+                if constexpr (m < NA - 1) store_slice<T>(pk + (k0 + m) * 128, s[m]);
+                else if (full) store_slice<T>(pk + (k0 + m) * 128, s[m]);
+            });
+        }
+    }
+}
+
+// ---------------------------------------------------------------------------------------------------
+// a15 Delta::delta / a16 Delta::undelta (src/delta.rs:24-45), warp-block layout.
+// ---------------------------------------------------------------------------------------------------
+template <class T, bool UNDO>
+__global__ void __launch_bounds__(kThreads)
+delta_warp_kernel(const char* __restrict__ in, const char* __restrict__ base, char* __restrict__ out, size_t n_blocks) {
+    using R = typename Lay<T>::R;
+    using WL = WarpLay<T>;
+    constexpr int TB = Lay<T>::TB;
+    constexpr int RPG = WL::RPG;
+    constexpr int NR = Lay<T>::NR;
+    const size_t blk = (size_t(blockIdx.x) * kThreads + threadIdx.x) >> 5;
+    if (blk >= n_blocks) return;
+    const int lane = threadIdx.x & 31;
+    const int g = lane >> 3, j = lane & 7;
+    const int q = WL::rank_of_group(g);
+    const char* ip = in + blk * (size_t(128) * TB) + j * 16;
+    char* op = out + blk * (size_t(128) * TB) + j * 16;
+    Slice<T> v[RPG];
+    seq_rows<RPG>([&](auto ic) {
+        constexpr int i = decltype(ic)::value;
+        v[i] = load_slice<T>(ip + warp_row_offset<T, i>(q));
+    });
+    Slice<T> carry = load_slice<T>(base + blk * 128 + j * 16);  // delta.rs:26 / :38: prev = base[lane]
+    if constexpr (UNDO) {
+#pragma unroll
+        for (int i = 1; i < RPG; ++i) v[i] = slice_add<T>(v[i], v[i - 1]);  // delta.rs:40-42 within the run
+#pragma unroll
+        for (int qq = 0; qq < 3; ++qq) {
+            const int srcl = WL::group_of_rank(qq) * 8 + j;
+#pragma unroll
+            for (int r = 0; r < NR; ++r) {
+                const R t = shfl_reg<R>(v[RPG - 1].r[r], srcl);
+                if (qq < q) carry.r[r] = lane_add<T>(carry.r[r], t);
+            }
+        }
+#pragma unroll
+        for (int i = 0; i < RPG; ++i) v[i] = slice_add<T>(v[i], carry);
+    } else {
+        // delta.rs:28-30: out = in - prev; prev of a run's first row is the previous run's last row
+        const int srcl = WL::group_of_rank(q > 0 ? q - 1 : 0) * 8 + j;
+        Slice<T> first_prev;
+#pragma unroll
+        for (int r = 0; r < NR; ++r) {
+            const R t = shfl_reg<R>(v[RPG - 1].r[r], srcl);
+            first_prev.r[r] = (q == 0) ? carry.r[r] : t;
+        }
+#pragma unroll
+        for (int i = RPG - 1; i >= 1; --i) v[i] = slice_sub<T>(v[i], v[i - 1]);
+        v[0] = slice_sub<T>(v[0], first_prev);
+    }
+    seq_rows<RPG>([&](auto ic) {
+        constexpr int i = decltype(ic)::value;
+        store_slice<T>(op + warp_row_offset<T, i>(q), v[i]);
+    });
+}
+
 // ---------------------------------------------------------------------------------------------------
 // pack family:  a7 BitPacking::pack (src/bitpacking.rs:65-74), a18 FoR::for_pack (src/ffor.rs:24-36).
 //   in : n_blocks x (128*T bytes)        packed : n_blocks x (128*W bytes)

@@ -76,12 +76,108 @@ transpose_kernel(const T* __restrict__ in, T* __restrict__ out, size_t n_blocks)
     }
 }
 
+// ---------------------------------------------------------------------------------------------------
+// u32 / u64 fast path: 16-byte-chunk tiles, zero shared-memory bank conflicts, no per-element traffic.
+// A thread owns the square tile  {EPC consecutive a} x {the EPC elements of one original chunk}  (EPC = 16/sizeof(T)):
+// it moves EPC original chunks <-> EPC transposed chunks and the EPC x EPC element transpose between them is a
+// pure register renaming.  The original-order side lives in shared memory with an XOR swizzle on the chunk
+// position (so both the linear fill/drain and the tile accesses are conflict-free); the transposed-order side is
+// accessed directly in global memory, a warp covering 512 contiguous bytes per instruction.
+//   u32: tile (ag,f,ch): chunks (a=4ag+e, f, c=4ch..4ch+3)  <->  chunks' (c=4ch+e', b=FL[f], a=4ag..4ag+3)
+//   u64: tile (ap,f,cq): chunks (a=2ap+e, f, c=2cq..2cq+1)  <->  chunks' (c=2cq+e', b=FL[f], a=2ap..2ap+1)
+// ---------------------------------------------------------------------------------------------------
+template <class T> struct TileCfg;
+template <> struct TileCfg<uint32_t> {
+    static constexpr int EPC = 4, BLOCKS = 8, TILES = 64, CHUNKS = 256;
+    // tile id -> (lane-major so that a warp's transposed chunks are contiguous): lane = ag*8 + f, warp = ch
+    __device__ static void decode(int tile, int& arow0, int& f, int& inner) { inner = tile >> 5; arow0 = ((tile >> 3) & 3) * 4; f = tile & 7; }
+    // swizzled position (16-byte units) of original chunk (a, f, inner) inside a block's 4 KiB tile
+    __device__ static int smem_chunk(int a, int f, int inner) { return 16 * a + ((2 * f + inner) ^ (f >> 2)); }
+    // swizzled position of LINEAR original chunk index x (x = 16a + 2f + ch)
+    __device__ static int smem_linear(int x) { const int v = x & 15; return (x & ~15) | (v ^ (v >> 3)); }
+    // transposed chunk index for element c of the tile
+    __device__ static int tr_chunk(int arow0, int f, int c) { return (arow0 >> 2) + 4 * fl_order(f) + 32 * c; }
+};
+template <> struct TileCfg<uint64_t> {
+    static constexpr int EPC = 2, BLOCKS = 4, TILES = 256, CHUNKS = 512;
+    // lane = bq*8 + ap, warp = (h, cq):  b = 4h + bq, f = FL[b]
+    __device__ static void decode(int tile, int& arow0, int& f, int& inner) {
+        const int ap = tile & 7, bq = (tile >> 3) & 3, h = (tile >> 5) & 1;
+        inner = tile >> 6; arow0 = 2 * ap; f = fl_order_rt(4 * h + bq);
+    }
+    __device__ static int smem_chunk(int a, int f, int inner) { return 32 * a + ((4 * f + inner) ^ ((a >> 1) & 7)); }
+    __device__ static int smem_linear(int x) { const int a = x >> 5; return (x & ~31) | ((x & 31) ^ ((a >> 1) & 7)); }
+    __device__ static int tr_chunk(int arow0, int f, int c) { return (arow0 >> 1) + 8 * fl_order_rt(f) + 64 * c; }
+};
+
+template <class T, bool UNDO>
+__global__ void __launch_bounds__(kTrThreads)
+transpose_tile_kernel(const T* __restrict__ in, T* __restrict__ out, size_t n_blocks) {
+    using C = TileCfg<T>;
+    constexpr int EPC = C::EPC;
+    __shared__ __align__(16) uint4 tile[C::BLOCKS][C::CHUNKS];
+    const size_t blk0 = size_t(blockIdx.x) * C::BLOCKS;
+    const int nb = int(min(size_t(C::BLOCKS), n_blocks - blk0));
+
+    if constexpr (!UNDO) {
+        // fill: original order, linear & coalesced, swizzled shared position
+        for (int x = threadIdx.x; x < nb * C::CHUNKS; x += kTrThreads) {
+            const int b = x / C::CHUNKS, q = x % C::CHUNKS;
+            tile[b][C::smem_linear(q)] = ldg128_stream(reinterpret_cast<const char*>(in + (blk0 + b) * 1024) + q * 16);
+        }
+        __syncthreads();
+    }
+    for (int t = threadIdx.x; t < nb * C::TILES; t += kTrThreads) {
+        const int b = t / C::TILES;
+        int arow0, f, inner;
+        C::decode(t % C::TILES, arow0, f, inner);
+        alignas(16) T m[EPC][EPC];  // m[e][k]: original chunk (a = arow0+e), element k  (c = inner*EPC + k)
+        if constexpr (!UNDO) {
+#pragma unroll
+            for (int e = 0; e < EPC; ++e) *reinterpret_cast<uint4*>(m[e]) = tile[b][C::smem_chunk(arow0 + e, f, inner)];
+            char* o = reinterpret_cast<char*>(out + (blk0 + b) * 1024);
+#pragma unroll
+            for (int k = 0; k < EPC; ++k) {
+                alignas(16) T v[EPC];
+#pragma unroll
+                for (int e = 0; e < EPC; ++e) v[e] = m[e][k];
+                stg128_stream(o + C::tr_chunk(arow0, f, inner * EPC + k) * 16, *reinterpret_cast<uint4*>(v));
+            }
+        } else {
+            const char* ip = reinterpret_cast<const char*>(in + (blk0 + b) * 1024);
+#pragma unroll
+            for (int k = 0; k < EPC; ++k) {
+                alignas(16) T v[EPC];
+                *reinterpret_cast<uint4*>(v) = ldg128_stream(ip + C::tr_chunk(arow0, f, inner * EPC + k) * 16);
+#pragma unroll
+                for (int e = 0; e < EPC; ++e) m[e][k] = v[e];
+            }
+#pragma unroll
+            for (int e = 0; e < EPC; ++e) tile[b][C::smem_chunk(arow0 + e, f, inner)] = *reinterpret_cast<uint4*>(m[e]);
+        }
+    }
+    if constexpr (UNDO) {
+        __syncthreads();
+        for (int x = threadIdx.x; x < nb * C::CHUNKS; x += kTrThreads) {
+            const int b = x / C::CHUNKS, q = x % C::CHUNKS;
+            stg128_stream(reinterpret_cast<char*>(out + (blk0 + b) * 1024) + q * 16, tile[b][C::smem_linear(q)]);
+        }
+    }
+}
+
 template <class T>
 cudaError_t launch_transpose(bool undo, const LaunchArgs& a) {
-    using C = TrCfg<T>;
-    const unsigned grid = unsigned((a.n_blocks + C::BLOCKS_PER_CTA - 1) / C::BLOCKS_PER_CTA);
     const T* in = static_cast<const T*>(a.in);
     T* out = static_cast<T*>(a.out);
+    if constexpr (sizeof(T) >= 4) {
+        using TC = TileCfg<T>;
+        const unsigned grid = unsigned((a.n_blocks + TC::BLOCKS - 1) / TC::BLOCKS);
+        if (undo) transpose_tile_kernel<T, true><<<grid, kTrThreads, 0, a.stream>>>(in, out, a.n_blocks);
+        else transpose_tile_kernel<T, false><<<grid, kTrThreads, 0, a.stream>>>(in, out, a.n_blocks);
+        return cudaGetLastError();
+    }
+    using C = TrCfg<T>;
+    const unsigned grid = unsigned((a.n_blocks + C::BLOCKS_PER_CTA - 1) / C::BLOCKS_PER_CTA);
     if (undo) transpose_kernel<T, true><<<grid, kTrThreads, 0, a.stream>>>(in, out, a.n_blocks);
     else transpose_kernel<T, false><<<grid, kTrThreads, 0, a.stream>>>(in, out, a.n_blocks);
     return cudaGetLastError();

@@ -104,6 +104,15 @@ static void bench_width(const Ctx& c, const std::string& op) {
     } else if (op == "undelta_pack") {
         float ms = time_ms(c, [&] { unpack_kernel<T, W, UOP_DELTA><<<grid, kThreads, 0, c.s>>>(c.in, c.out, c.n_blocks, nullptr, T(0), c.base); });
         report("undelta_pack", TB, W, c.n_blocks, 128 * (W + TB + 1), ms);
+    } else if (op == "packB" || op == "for_packB") {
+        const unsigned gridB = unsigned((c.n_blocks * 32 + kThreads - 1) / kThreads);
+        if (op == "packB") {
+            float ms = time_ms(c, [&] { pack_warp_kernel<T, W, POP_PLAIN><<<gridB, kThreads, 0, c.s>>>(c.out, c.in, c.n_blocks, nullptr, T(0)); });
+            report("packB", TB, W, c.n_blocks, 128 * (W + TB), ms);
+        } else {
+            float ms = time_ms(c, [&] { pack_warp_kernel<T, W, POP_FOR><<<gridB, kThreads, 0, c.s>>>(c.out, c.in, c.n_blocks, nullptr, T(12345)); });
+            report("for_packB", TB, W, c.n_blocks, 128 * (W + TB), ms);
+        }
     } else if (op == "pack") {
         // input = the "out" buffer (unpacked side), output = the "in" buffer (packed side)
         float ms = time_ms(c, [&] { pack_kernel<T, W, POP_PLAIN><<<grid, kThreads, 0, c.s>>>(c.out, c.in, c.n_blocks, nullptr, T(0)); });
@@ -123,6 +132,15 @@ template <class T>
 static void run_type(Ctx& c, const std::string& op, int lo, int hi) {
     constexpr int TB = Lay<T>::TB;
     const unsigned grid = unsigned((c.n_blocks * kSlicesPerBlock + kThreads - 1) / kThreads);
+    if (op == "deltaB" || op == "undeltaB") {
+        const unsigned gridB = unsigned((c.n_blocks * 32 + kThreads - 1) / kThreads);
+        char* tmp = c.in;
+        float ms = (op == "deltaB")
+            ? time_ms(c, [&] { delta_warp_kernel<T, false><<<gridB, kThreads, 0, c.s>>>(c.out, c.base, tmp, c.n_blocks); })
+            : time_ms(c, [&] { delta_warp_kernel<T, true><<<gridB, kThreads, 0, c.s>>>(c.out, c.base, tmp, c.n_blocks); });
+        report(op.c_str(), TB, 0, c.n_blocks, 128 * (2 * TB + 1), ms);
+        return;
+    }
     if (op == "delta" || op == "undelta") {
         char* tmp = c.in;  // both sides are unpacked-size: in buffer is sized for W = TB
         float ms = (op == "delta")

@@ -1,0 +1,83 @@
+#!/usr/bin/env python
+"""tools/opbench.py — every op x type through the shipped C ABI (device family), CUDA-event timed.
+Prints a table (algorithmic GB/s, Gint/s) and writes gpurun_out/opbench.json.  Development/measurement tool."""
+import json
+import os
+import statistics
+import sys
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+
+import torch  # noqa: E402
+
+from fastlanes_b200 import _lib  # noqa: E402
+
+TDT = {8: torch.uint8, 16: torch.int16, 32: torch.int32, 64: torch.int64}
+
+
+def timeit(fn, iters=7):
+    for _ in range(3):
+        fn()
+    torch.cuda.synchronize()
+    ts = []
+    for _ in range(iters):
+        a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        a.record(); fn(); b.record(); b.synchronize()
+        ts.append(a.elapsed_time(b))
+    return statistics.median(ts)
+
+
+def main():
+    lg_bytes = 32  # 4 GiB unpacked per type
+    rows = []
+    sp = torch.cuda.current_stream().cuda_stream
+    for tb in (8, 16, 32, 64):
+        n = (1 << lg_bytes) // (128 * tb)
+        unp = torch.empty(n * 1024, dtype=TDT[tb], device="cuda")
+        unp.view(torch.int32).random_(-(1 << 31), (1 << 31) - 1)
+        pk = torch.empty(n * 1024, dtype=TDT[tb], device="cuda")
+        pk.view(torch.int32).random_(-(1 << 31), (1 << 31) - 1)
+        base = torch.empty(n * (1024 // tb), dtype=TDT[tb], device="cuda")
+        base.view(torch.int32).random_(-(1 << 31), (1 << 31) - 1)
+        U, P, B = unp.data_ptr(), pk.data_ptr(), base.data_ptr()
+        widths = sorted({1, tb // 4, tb // 2 + 1, tb - 3, tb})
+
+        def rec(op, w, bytes_per_block, fn):
+            st = fn()
+            assert st == 0, (op, tb, w, st)
+            ms = timeit(fn)
+            rows.append({"op": op, "T": tb, "W": w, "blocks": n, "us": round(ms * 1e3, 1),
+                         "GBps": round(n * bytes_per_block / (ms * 1e-3) / 1e9, 1),
+                         "Gints": round(n * 1024 / (ms * 1e-3) / 1e9, 1)})
+            r = rows[-1]
+            print(f"{op:14s} u{tb:<2d} W={w:<2d} {r['us']:9.1f} us {r['GBps']:8.1f} GB/s {r['Gints']:8.1f} Gint/s", flush=True)
+
+        for w in widths:
+            rec("unpack", w, 128 * (w + tb), lambda: _lib.fn("fl_unpack", tb)(w, n, P, U, sp))
+            rec("pack", w, 128 * (w + tb), lambda: _lib.fn("fl_pack", tb)(w, n, U, P, sp))
+            rec("unfor_pack", w, 128 * (w + tb), lambda: _lib.fn("fl_unfor_pack", tb)(w, n, P, 12345 % (1 << tb), U, sp))
+            rec("for_pack", w, 128 * (w + tb), lambda: _lib.fn("fl_for_pack", tb)(w, n, U, 12345 % (1 << tb), P, sp))
+            rec("undelta_pack", w, 128 * (w + tb + 1), lambda: _lib.fn("fl_undelta_pack", tb)(w, n, P, B, U, sp))
+        rec("delta", 0, 128 * (2 * tb + 1), lambda: _lib.fn("fl_delta", tb)(n, U, B, P, sp))
+        rec("undelta", 0, 128 * (2 * tb + 1), lambda: _lib.fn("fl_undelta", tb)(n, U, B, P, sp))
+        rec("transpose", 0, 256 * tb, lambda: _lib.fn("fl_transpose", tb)(n, U, P, sp))
+        rec("untranspose", 0, 256 * tb, lambda: _lib.fn("fl_untranspose", tb)(n, U, P, sp))
+        # batched unpack_single: 2^24 random queries
+        nq = 1 << 24
+        gi = torch.randint(0, n * 1024, (nq,), dtype=torch.int64, device="cuda")
+        qo = torch.empty(nq, dtype=TDT[tb], device="cuda")
+        w = tb // 2 + 1
+        fn = lambda: _lib.fn("fl_unpack_gather", tb)(w, n, P, gi.data_ptr(), nq, qo.data_ptr(), None, sp)
+        assert fn() == 0
+        ms = timeit(fn)
+        rows.append({"op": "unpack_gather", "T": tb, "W": w, "queries": nq, "us": round(ms * 1e3, 1), "Gq_per_s": round(nq / (ms * 1e-3) / 1e9, 2)})
+        print(f"unpack_gather  u{tb:<2d} W={w:<2d} {ms * 1e3:9.1f} us {nq / (ms * 1e-3) / 1e9:8.2f} Gqueries/s", flush=True)
+        del unp, pk, base, gi, qo
+        torch.cuda.empty_cache()
+    os.makedirs(os.path.join(ROOT, "gpurun_out"), exist_ok=True)
+    json.dump(rows, open(os.path.join(ROOT, "gpurun_out", "opbench.json"), "w"), indent=0)
+
+
+if __name__ == "__main__":
+    main()
