@@ -10,7 +10,7 @@ import os
 _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(_HERE, "lib", "libfastlanes_b200.so")
 
-FL_OK, FL_ERR_WIDTH, FL_ERR_LEN, FL_ERR_INDEX, FL_ERR_ALIGN, FL_ERR_CUDA, FL_ERR_NULL = range(7)
+FL_OK, FL_ERR_WIDTH, FL_ERR_LEN, FL_ERR_INDEX, FL_ERR_ALIGN, FL_ERR_CUDA, FL_ERR_NULL, FL_ERR_UNSUPPORTED = range(8)
 
 TYPE_SUFFIXES = {8: "u8", 16: "u16", 32: "u32", 64: "u64"}
 _CT = {8: ctypes.c_uint8, 16: ctypes.c_uint16, 32: ctypes.c_uint32, 64: ctypes.c_uint64}
@@ -25,6 +25,8 @@ _PER_TYPE = {
     "fl_delta": "nppps".replace(" ", ""), "fl_host_delta": "nppp",
     "fl_undelta": "nppps", "fl_host_undelta": "nppp",
     "fl_undelta_pack": "wnppps", "fl_host_undelta_pack": "wnppp",
+    "fl_undelta_pack_untranspose": "wnppps", "fl_host_undelta_pack_untranspose": "wnppp",
+    "fl_transpose_delta_pack": "wnppps", "fl_host_transpose_delta_pack": "wnppp",
     "fl_transpose": "npps", "fl_untranspose": "npps",
     "fl_host_transpose": "npp", "fl_host_untranspose": "npp",
 }

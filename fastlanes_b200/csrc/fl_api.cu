@@ -35,14 +35,21 @@ fl_status cuda_fail(cudaError_t e, const char* where) {
 
 inline bool aligned16(const void* p) { return (reinterpret_cast<uintptr_t>(p) & 15u) == 0; }
 
-enum class Op { Pack, Unpack, ForPack, UnforPack, Delta, Undelta, UndeltaPack, Transpose, Untranspose };
+enum class Op { Pack, Unpack, ForPack, UnforPack, Delta, Undelta, UndeltaPack, Transpose, Untranspose,
+                UndeltaPackUntranspose, TransposeDeltaPack };
 
 inline bool op_has_width(Op op) {
-    return op == Op::Pack || op == Op::Unpack || op == Op::ForPack || op == Op::UnforPack || op == Op::UndeltaPack;
+    return op == Op::Pack || op == Op::Unpack || op == Op::ForPack || op == Op::UnforPack || op == Op::UndeltaPack ||
+           op == Op::UndeltaPackUntranspose || op == Op::TransposeDeltaPack;
 }
-inline bool op_input_packed(Op op) { return op == Op::Unpack || op == Op::UnforPack || op == Op::UndeltaPack; }
-inline bool op_output_packed(Op op) { return op == Op::Pack || op == Op::ForPack; }
-inline bool op_has_base(Op op) { return op == Op::Delta || op == Op::Undelta || op == Op::UndeltaPack; }
+inline bool op_input_packed(Op op) {
+    return op == Op::Unpack || op == Op::UnforPack || op == Op::UndeltaPack || op == Op::UndeltaPackUntranspose;
+}
+inline bool op_output_packed(Op op) { return op == Op::Pack || op == Op::ForPack || op == Op::TransposeDeltaPack; }
+inline bool op_has_base(Op op) {
+    return op == Op::Delta || op == Op::Undelta || op == Op::UndeltaPack || op == Op::UndeltaPackUntranspose ||
+           op == Op::TransposeDeltaPack;
+}
 
 // bytes per block on each side
 inline size_t in_block_bytes(Op op, unsigned tbits, unsigned width) {
@@ -57,6 +64,8 @@ fl_status device_op(Op op, unsigned width, size_t n_blocks, const void* in, void
                     const void* refs, uint64_t ref_scalar, cudaStream_t stream) {
     constexpr unsigned TB = sizeof(T) * 8;
     if (op_has_width(op) && width > TB) return fail(FL_ERR_WIDTH, "width exceeds the bit size of the element type");
+    if ((op == Op::UndeltaPackUntranspose || op == Op::TransposeDeltaPack) && sizeof(T) < 4)
+        return fail(FL_ERR_UNSUPPORTED, "fused original-order ops are implemented for u32/u64");
     if (!op_has_width(op)) width = 0;
     if (n_blocks == 0) return FL_OK;
     if (n_blocks > (size_t(1) << 40)) return fail(FL_ERR_LEN, "n_blocks too large");
@@ -78,6 +87,8 @@ fl_status device_op(Op op, unsigned width, size_t n_blocks, const void* in, void
         case Op::Unpack: e = flb::launch_unpack<T>(flb::kUnpackPlain, a); break;
         case Op::UnforPack: e = flb::launch_unpack<T>(flb::kUnpackFor, a); break;
         case Op::UndeltaPack: e = flb::launch_unpack<T>(flb::kUnpackDelta, a); break;
+        case Op::UndeltaPackUntranspose: e = flb::launch_unpack<T>(flb::kUnpackDeltaOrig, a); break;
+        case Op::TransposeDeltaPack: e = flb::launch_pack<T>(flb::kPackOrigDelta, a); break;
         case Op::Delta: e = flb::launch_delta<T>(false, a); break;
         case Op::Undelta: e = flb::launch_delta<T>(true, a); break;
         case Op::Transpose: e = flb::launch_transpose<T>(false, a); break;
@@ -134,6 +145,8 @@ fl_status host_op(Op op, unsigned width, size_t n_blocks, const void* in, void* 
                   uint64_t ref_scalar) {
     constexpr unsigned TB = sizeof(T) * 8;
     if (op_has_width(op) && width > TB) return fail(FL_ERR_WIDTH, "width exceeds the bit size of the element type");
+    if ((op == Op::UndeltaPackUntranspose || op == Op::TransposeDeltaPack) && sizeof(T) < 4)
+        return fail(FL_ERR_UNSUPPORTED, "fused original-order ops are implemented for u32/u64");
     if (!op_has_width(op)) width = 0;
     if (n_blocks == 0) return FL_OK;
     const size_t ib = in_block_bytes(op, TB, width), ob = out_block_bytes(op, TB, width);
@@ -236,6 +249,7 @@ const char* fl_status_string(fl_status s) {
         case FL_ERR_ALIGN: return "FL_ERR_ALIGN";
         case FL_ERR_CUDA: return "FL_ERR_CUDA";
         case FL_ERR_NULL: return "FL_ERR_NULL";
+        case FL_ERR_UNSUPPORTED: return "FL_ERR_UNSUPPORTED";
         default: return "FL_ERR_UNKNOWN";
     }
 }
@@ -353,6 +367,19 @@ fl_status fl_shutdown(void) {
     }                                                                                                                   \
     fl_status fl_host_undelta_pack_##SFX(unsigned width, size_t n, const T* packed, const T* base, T* out) {            \
         return host_op<T>(Op::UndeltaPack, width, n, packed, out, base, 0);                                             \
+    }                                                                                                                   \
+    fl_status fl_undelta_pack_untranspose_##SFX(unsigned width, size_t n, const T* packed, const T* base, T* out,       \
+                                                void* st) {                                                            \
+        return device_op<T>(Op::UndeltaPackUntranspose, width, n, packed, out, base, nullptr, 0, (cudaStream_t)st);     \
+    }                                                                                                                   \
+    fl_status fl_host_undelta_pack_untranspose_##SFX(unsigned width, size_t n, const T* packed, const T* base, T* out) { \
+        return host_op<T>(Op::UndeltaPackUntranspose, width, n, packed, out, base, 0);                                  \
+    }                                                                                                                   \
+    fl_status fl_transpose_delta_pack_##SFX(unsigned width, size_t n, const T* in, const T* base, T* packed, void* st) { \
+        return device_op<T>(Op::TransposeDeltaPack, width, n, in, packed, base, nullptr, 0, (cudaStream_t)st);          \
+    }                                                                                                                   \
+    fl_status fl_host_transpose_delta_pack_##SFX(unsigned width, size_t n, const T* in, const T* base, T* packed) {     \
+        return host_op<T>(Op::TransposeDeltaPack, width, n, in, packed, base, 0);                                       \
     }                                                                                                                   \
     fl_status fl_transpose_##SFX(size_t n, const T* in, T* out, void* st) {                                             \
         return device_op<T>(Op::Transpose, 0, n, in, out, nullptr, nullptr, 0, (cudaStream_t)st);                       \

@@ -39,16 +39,28 @@ template <class T, int OP, int... W>
 static constexpr std::array<launch_fn, sizeof...(W)> unpack_table(std::integer_sequence<int, W...>) {
     return {{&do_unpack<T, W, OP>...}};
 }
+// fused undelta_pack + untranspose: u32/u64 only this round (dependent context so that `if constexpr` discards)
+template <class T>
+static cudaError_t unpack_delta_orig(const LaunchArgs& a) {
+    if constexpr (sizeof(T) >= 4) {
+        static constexpr auto tab = unpack_table<T, UOP_DELTA_ORIG>(std::make_integer_sequence<int, Lay<T>::TB + 1>{});
+        return tab[a.width](a);
+    } else {
+        return cudaErrorNotSupported;
+    }
+}
 template <>
 cudaError_t launch_unpack<elem_t>(int op, const LaunchArgs& a) {
     using seq = std::make_integer_sequence<int, Lay<elem_t>::TB + 1>;
     static constexpr auto plain = unpack_table<elem_t, UOP_PLAIN>(seq{});
     static constexpr auto ffor = unpack_table<elem_t, UOP_FOR>(seq{});
     static constexpr auto delta = unpack_table<elem_t, UOP_DELTA>(seq{});
+    if (op == kUnpackDeltaOrig) return unpack_delta_orig<elem_t>(a);
     switch (op) {
         case kUnpackPlain: return plain[a.width](a);
         case kUnpackFor: return ffor[a.width](a);
-        default: return delta[a.width](a);
+        case kUnpackDelta: return delta[a.width](a);
+        default: return cudaErrorNotSupported;
     }
 }
 #elif FLB_PART == 1
@@ -57,19 +69,32 @@ static cudaError_t do_pack(const LaunchArgs& a) {
     const unsigned grid = unsigned((a.n_blocks * 32 + kThreads - 1) / kThreads);  // warp-block layout
     pack_warp_kernel<T, W, OP><<<grid, kThreads, 0, a.stream>>>(
         static_cast<const char*>(a.in), static_cast<char*>(a.out), a.n_blocks, static_cast<const T*>(a.refs),
-        T(a.ref_scalar));
+        T(a.ref_scalar), static_cast<const char*>(a.base));
     return cudaGetLastError();
 }
 template <class T, int OP, int... W>
 static constexpr std::array<launch_fn, sizeof...(W)> pack_table(std::integer_sequence<int, W...>) {
     return {{&do_pack<T, W, OP>...}};
 }
+// fused transpose + delta + pack: u32/u64 only this round
+template <class T>
+static cudaError_t pack_orig_delta(const LaunchArgs& a) {
+    if constexpr (sizeof(T) >= 4) {
+        static constexpr auto tab = pack_table<T, POP_ORIG_DELTA>(std::make_integer_sequence<int, Lay<T>::TB + 1>{});
+        return tab[a.width](a);
+    } else {
+        return cudaErrorNotSupported;
+    }
+}
 template <>
 cudaError_t launch_pack<elem_t>(int op, const LaunchArgs& a) {
     using seq = std::make_integer_sequence<int, Lay<elem_t>::TB + 1>;
     static constexpr auto plain = pack_table<elem_t, POP_PLAIN>(seq{});
     static constexpr auto ffor = pack_table<elem_t, POP_FOR>(seq{});
-    return (op == kPackPlain ? plain : ffor)[a.width](a);
+    if (op == kPackOrigDelta) return pack_orig_delta<elem_t>(a);
+    if (op == kPackPlain) return plain[a.width](a);
+    if (op == kPackFor) return ffor[a.width](a);
+    return cudaErrorNotSupported;
 }
 #else
 template <>

@@ -14,8 +14,10 @@
 
 namespace flb {
 
-enum UnpackOp : int { UOP_PLAIN = 0, UOP_FOR = 1, UOP_DELTA = 2 };
-enum PackOp : int { POP_PLAIN = 0, POP_FOR = 1 };
+// UOP_DELTA_ORIG: fused undelta_pack + untranspose (output in ORIGINAL value order)  — SURVEY.md §8(f) rank 1
+// POP_ORIG_DELTA: fused transpose + delta + pack   (input  in ORIGINAL value order)
+enum UnpackOp : int { UOP_PLAIN = 0, UOP_FOR = 1, UOP_DELTA = 2, UOP_DELTA_ORIG = 3 };
+enum PackOp : int { POP_PLAIN = 0, POP_FOR = 1, POP_ORIG_DELTA = 2 };
 
 #ifndef FLB_THREADS
 #define FLB_THREADS 256
@@ -146,6 +148,70 @@ __device__ __forceinline__ typename Lay<T>::R lane_funnel_rt(typename Lay<T>::R 
     }
 }
 
+// byte offset of local row i of the run of rank q (global row r = q*RPG + i), see row_byte_offset()
+template <class T, int I>
+__device__ __forceinline__ int warp_row_offset(int q) {
+    constexpr int RPG = WarpLay<T>::RPG;
+    if constexpr (RPG >= 8) {
+        const int oidx = q * (RPG / 8) + I / 8;  // r/8 ; r%8 = I%8
+        return (fl_order_rt(oidx) * 16 + (I % 8) * 128) * int(sizeof(T));
+    } else {
+        const int r = q * RPG + I;
+        return (fl_order_rt(r >> 3) * 16 + (r & 7) * 128) * int(sizeof(T));
+    }
+}
+
+// Original-order placement (src/transpose.rs:29-36 composed with src/macros.rs:20-24): lane l of the transposed
+// vector walks T CONSECUTIVE originals starting at start(l) = 64*(l%16) + 8*FL_ORDER[l/16], so
+// the RPG rows a thread holds for one lane are RPG consecutive originals.  Byte offset of that run inside the
+// block, for SWAR register r of slice j in the run of rank q (u32/u64 only: one lane per register):
+template <class T>
+__device__ __forceinline__ int orig_run_byte_offset(int q, int j, int r) {
+    static_assert(sizeof(T) >= 4, "original-order fused ops are implemented for u32/u64");
+    const int l = Lay<T>::NR * j + r;
+    return (64 * (l & 15) + 8 * fl_order_rt(l >> 4) + q * WarpLay<T>::RPG) * int(sizeof(T));
+}
+// chunk m (16 bytes = EPC consecutive rows) of lane-register r out of the row-major register tile v[row].r[r]
+template <class T, int RPG>
+__device__ __forceinline__ uint4 gather_rows_chunk(const Slice<T> (&v)[RPG], int r, int m) {
+    if constexpr (sizeof(T) == 4) {
+        return make_uint4(v[4 * m].r[r], v[4 * m + 1].r[r], v[4 * m + 2].r[r], v[4 * m + 3].r[r]);
+    } else {
+        const uint64_t a = v[2 * m].r[r], b = v[2 * m + 1].r[r];
+        return make_uint4(uint32_t(a), uint32_t(a >> 32), uint32_t(b), uint32_t(b >> 32));
+    }
+}
+template <class T, int RPG>
+__device__ __forceinline__ void scatter_rows_chunk(Slice<T> (&v)[RPG], int r, int m, uint4 c) {
+    if constexpr (sizeof(T) == 4) {
+        v[4 * m].r[r] = c.x; v[4 * m + 1].r[r] = c.y; v[4 * m + 2].r[r] = c.z; v[4 * m + 3].r[r] = c.w;
+    } else {
+        v[2 * m].r[r] = (uint64_t(c.y) << 32) | c.x;
+        v[2 * m + 1].r[r] = (uint64_t(c.w) << 32) | c.z;
+    }
+}
+
+template <class R>
+__device__ __forceinline__ R shfl_reg(R v, int src) {
+    if constexpr (sizeof(R) == 8) return R(__shfl_sync(0xffffffffu, (unsigned long long)v, src));
+    else return R(__shfl_sync(0xffffffffu, v, src));
+}
+
+// lane-wise funnel shift LEFT by a run-time amount sh (0 <= sh < T): (hi << sh) | (lo >> (T - sh))
+template <class T>
+__device__ __forceinline__ typename Lay<T>::R lane_funnel_left_rt(typename Lay<T>::R lo, typename Lay<T>::R hi, unsigned sh,
+                                                                  typename Lay<T>::R mlow) {
+    using R = typename Lay<T>::R;
+    if constexpr (sizeof(T) == 4) {
+        return __funnelshift_l(lo, hi, sh);
+    } else if constexpr (sizeof(T) == 8) {
+        return (hi << sh) | ((lo >> 1) >> (63u - sh));
+    } else {
+        constexpr unsigned TBu = Lay<T>::TB;
+        return ((hi << sh) & R(~mlow)) | ((lo >> (TBu - sh)) & mlow);  // mlow = low `sh` bits of every lane
+    }
+}
+
 template <class T, int W, int OP>
 __global__ void __launch_bounds__(kThreads)
 unpack_warp_kernel(const char* __restrict__ packed, char* __restrict__ out, size_t n_blocks,
@@ -213,7 +279,7 @@ unpack_warp_kernel(const char* __restrict__ packed, char* __restrict__ out, size
 #pragma unroll
         for (int i = 0; i < RPG; ++i) v[i] = slice_add<T>(v[i], ref);
     }
-    if constexpr (OP == UOP_DELTA) {
+    if constexpr (OP == UOP_DELTA || OP == UOP_DELTA_ORIG) {
         // delta.rs:56-60: running wrapping sum along rows per lane, seeded with base[lane]
 #pragma unroll
         for (int i = 1; i < RPG; ++i) v[i] = slice_add<T>(v[i], v[i - 1]);
@@ -232,6 +298,19 @@ unpack_warp_kernel(const char* __restrict__ packed, char* __restrict__ out, size
 #pragma unroll
         for (int i = 0; i < RPG; ++i) v[i] = slice_add<T>(v[i], carry);
     }
+    if constexpr (OP == UOP_DELTA_ORIG) {
+        // untranspose fused into the store (transpose.rs:18-22): per lane, the RPG rows are RPG consecutive
+        // originals -> RPG*sizeof(T)/16 contiguous 16-byte chunks; the row->chunk regrouping is register renaming.
+        constexpr int EPC = 16 / int(sizeof(T));
+        char* ob = out + blk * (size_t(128) * TB);
+#pragma unroll
+        for (int r = 0; r < NR; ++r) {
+            char* po = ob + orig_run_byte_offset<T>(q, j, r);
+#pragma unroll
+            for (int m = 0; m < RPG / EPC; ++m) stg128_stream(po + m * 16, gather_rows_chunk<T, RPG>(v, r, m));
+        }
+        return;
+    }
     seq_rows<RPG>([&](auto ic) {
         constexpr int i = decltype(ic)::value;
         // global row r = q*RPG + i: offset (FL_ORDER[r/8]*16 + (r%8)*128)*sizeof(T)  (macros.rs:20-24)
@@ -248,40 +327,6 @@ unpack_warp_kernel(const char* __restrict__ packed, char* __restrict__ out, size
     });
 }
 
-// byte offset of local row i of the run of rank q (global row r = q*RPG + i), see row_byte_offset()
-template <class T, int I>
-__device__ __forceinline__ int warp_row_offset(int q) {
-    constexpr int RPG = WarpLay<T>::RPG;
-    if constexpr (RPG >= 8) {
-        const int oidx = q * (RPG / 8) + I / 8;  // r/8 ; r%8 = I%8
-        return (fl_order_rt(oidx) * 16 + (I % 8) * 128) * int(sizeof(T));
-    } else {
-        const int r = q * RPG + I;
-        return (fl_order_rt(r >> 3) * 16 + (r & 7) * 128) * int(sizeof(T));
-    }
-}
-
-template <class R>
-__device__ __forceinline__ R shfl_reg(R v, int src) {
-    if constexpr (sizeof(R) == 8) return R(__shfl_sync(0xffffffffu, (unsigned long long)v, src));
-    else return R(__shfl_sync(0xffffffffu, v, src));
-}
-
-// lane-wise funnel shift LEFT by a run-time amount sh (0 <= sh < T): (hi << sh) | (lo >> (T - sh))
-template <class T>
-__device__ __forceinline__ typename Lay<T>::R lane_funnel_left_rt(typename Lay<T>::R lo, typename Lay<T>::R hi, unsigned sh,
-                                                                  typename Lay<T>::R mlow) {
-    using R = typename Lay<T>::R;
-    if constexpr (sizeof(T) == 4) {
-        return __funnelshift_l(lo, hi, sh);
-    } else if constexpr (sizeof(T) == 8) {
-        return (hi << sh) | ((lo >> 1) >> (63u - sh));
-    } else {
-        constexpr unsigned TBu = Lay<T>::TB;
-        return ((hi << sh) & R(~mlow)) | ((lo >> (TBu - sh)) & mlow);  // mlow = low `sh` bits of every lane
-    }
-}
-
 // ---------------------------------------------------------------------------------------------------
 // pack family, warp-block layout: a7 BitPacking::pack (src/bitpacking.rs:65-74), a18 FoR::for_pack
 // (src/ffor.rs:24-36).  Same thread mapping as unpack_warp_kernel.  Each group packs its T/4 rows into an
@@ -292,7 +337,7 @@ __device__ __forceinline__ typename Lay<T>::R lane_funnel_left_rt(typename Lay<T
 template <class T, int W, int OP>
 __global__ void __launch_bounds__(kThreads)
 pack_warp_kernel(const char* __restrict__ in, char* __restrict__ packed, size_t n_blocks,
-                 const T* __restrict__ refs, T ref_scalar) {
+                 const T* __restrict__ refs, T ref_scalar, const char* __restrict__ base) {
     using R = typename Lay<T>::R;
     using WL = WarpLay<T>;
     constexpr int TB = Lay<T>::TB;
@@ -308,10 +353,33 @@ pack_warp_kernel(const char* __restrict__ in, char* __restrict__ packed, size_t 
     char* pk = packed + blk * (size_t(128) * W) + j * 16;
 
     Slice<T> src[RPG];
-    seq_rows<RPG>([&](auto ic) {
-        constexpr int i = decltype(ic)::value;
-        src[i] = load_slice<T>(ip + warp_row_offset<T, i>(q));
-    });
+    if constexpr (OP == POP_ORIG_DELTA) {
+        // transpose fused into the load (transpose.rs:11-15), then delta along rows (delta.rs:24-33)
+        constexpr int EPC = 16 / int(sizeof(T));
+        const char* ib = in + blk * (size_t(128) * TB);
+#pragma unroll
+        for (int r = 0; r < NR; ++r) {
+            const char* pi = ib + orig_run_byte_offset<T>(q, j, r);
+#pragma unroll
+            for (int m = 0; m < RPG / EPC; ++m) scatter_rows_chunk<T, RPG>(src, r, m, ldg128_stream(pi + m * 16));
+        }
+        const Slice<T> b0 = load_slice<T>(base + blk * 128 + j * 16);  // base[lane]
+        const int srcl = WL::group_of_rank(q > 0 ? q - 1 : 0) * 8 + j;
+        Slice<T> first_prev;
+#pragma unroll
+        for (int r = 0; r < NR; ++r) {
+            const R t = shfl_reg<R>(src[RPG - 1].r[r], srcl);
+            first_prev.r[r] = (q == 0) ? b0.r[r] : t;
+        }
+#pragma unroll
+        for (int i = RPG - 1; i >= 1; --i) src[i] = slice_sub<T>(src[i], src[i - 1]);
+        src[0] = slice_sub<T>(src[0], first_prev);
+    } else {
+        seq_rows<RPG>([&](auto ic) {
+            constexpr int i = decltype(ic)::value;
+            src[i] = load_slice<T>(ip + warp_row_offset<T, i>(q));
+        });
+    }
     if constexpr (OP == POP_FOR) {
         const Slice<T> ref = slice_splat<T>(refs ? refs[blk] : ref_scalar);  // ffor.rs:33
 #pragma unroll

@@ -88,7 +88,7 @@ transpose_kernel(const T* __restrict__ in, T* __restrict__ out, size_t n_blocks)
 // ---------------------------------------------------------------------------------------------------
 template <class T> struct TileCfg;
 template <> struct TileCfg<uint32_t> {
-    static constexpr int EPC = 4, BLOCKS = 8, TILES = 64, CHUNKS = 256;
+    static constexpr int EPC = 4, BLOCKS = 8, TILES = 64, CHUNKS = 256, PAD = 0;
     // tile id -> (lane-major so that a warp's transposed chunks are contiguous): lane = ag*8 + f, warp = ch
     __device__ static void decode(int tile, int& arow0, int& f, int& inner) { inner = tile >> 5; arow0 = ((tile >> 3) & 3) * 4; f = tile & 7; }
     // swizzled position (16-byte units) of original chunk (a, f, inner) inside a block's 4 KiB tile
@@ -99,7 +99,7 @@ template <> struct TileCfg<uint32_t> {
     __device__ static int tr_chunk(int arow0, int f, int c) { return (arow0 >> 2) + 4 * fl_order(f) + 32 * c; }
 };
 template <> struct TileCfg<uint64_t> {
-    static constexpr int EPC = 2, BLOCKS = 4, TILES = 256, CHUNKS = 512;
+    static constexpr int EPC = 2, BLOCKS = 4, TILES = 256, CHUNKS = 512, PAD = 0;
     // lane = bq*8 + ap, warp = (h, cq):  b = 4h + bq, f = FL[b]
     __device__ static void decode(int tile, int& arow0, int& f, int& inner) {
         const int ap = tile & 7, bq = (tile >> 3) & 3, h = (tile >> 5) & 1;
@@ -110,12 +110,32 @@ template <> struct TileCfg<uint64_t> {
     __device__ static int tr_chunk(int arow0, int f, int c) { return (arow0 >> 1) + 8 * fl_order_rt(f) + 64 * c; }
 };
 
+//   u16: tile (ah,f):    chunks (a=8ah+e, f, c=0..7)             <->  chunks' (c, b=FL[f], a=8ah..8ah+7)   (8x8 halfwords)
+//   u8 : tile (fp):      chunks (a=e, f=2fp..2fp+1, c=0..7)       <->  chunks' (c, b=FL[f], a=0..15)        (16x16 bytes)
+// (for u8/u16 the element transpose is no longer free: the compiler emits PRMT byte permutes, ~1 per output byte/2.)
+template <> struct TileCfg<uint16_t> {
+    static constexpr int EPC = 8, BLOCKS = 16, TILES = 16, CHUNKS = 128, PAD = 0;
+    __device__ static void decode(int tile, int& arow0, int& f, int& inner) { inner = 0; arow0 = (tile >> 3) * 8; f = tile & 7; }
+    __device__ static int smem_chunk(int a, int f, int) { return 8 * a + f; }  // quarter-warp = 8 consecutive f: conflict-free
+    __device__ static int smem_linear(int x) { return x; }
+    __device__ static int tr_chunk(int arow0, int f, int c) { return (arow0 >> 3) + 2 * fl_order_rt(f) + 16 * c; }
+};
+template <> struct TileCfg<uint8_t> {
+    // PAD: 4 chunks of skew per block so that the two blocks sharing a quarter-warp hit different bank groups
+    static constexpr int EPC = 16, BLOCKS = 32, TILES = 4, CHUNKS = 64, PAD = 4;
+    __device__ static void decode(int tile, int& arow0, int& f, int& inner) { inner = 0; arow0 = 0; f = tile; }  // f := fp
+    __device__ static int smem_chunk(int a, int fp, int) { return 4 * a + fp; }
+    __device__ static int smem_linear(int x) { return x; }
+    // element x of the original chunk is (f = 2fp + x/8, c = x%8); transposed chunk index = b + 8c
+    __device__ static int tr_chunk(int, int fp, int x) { return fl_order_rt(2 * fp + (x >> 3)) + 8 * (x & 7); }
+};
+
 template <class T, bool UNDO>
 __global__ void __launch_bounds__(kTrThreads)
 transpose_tile_kernel(const T* __restrict__ in, T* __restrict__ out, size_t n_blocks) {
     using C = TileCfg<T>;
     constexpr int EPC = C::EPC;
-    __shared__ __align__(16) uint4 tile[C::BLOCKS][C::CHUNKS];
+    __shared__ __align__(16) uint4 tile[C::BLOCKS][C::CHUNKS + C::PAD];
     const size_t blk0 = size_t(blockIdx.x) * C::BLOCKS;
     const int nb = int(min(size_t(C::BLOCKS), n_blocks - blk0));
 
@@ -169,7 +189,7 @@ template <class T>
 cudaError_t launch_transpose(bool undo, const LaunchArgs& a) {
     const T* in = static_cast<const T*>(a.in);
     T* out = static_cast<T*>(a.out);
-    if constexpr (sizeof(T) >= 4) {
+    if constexpr (sizeof(T) >= 1) {
         using TC = TileCfg<T>;
         const unsigned grid = unsigned((a.n_blocks + TC::BLOCKS - 1) / TC::BLOCKS);
         if (undo) transpose_tile_kernel<T, true><<<grid, kTrThreads, 0, a.stream>>>(in, out, a.n_blocks);

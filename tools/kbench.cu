@@ -107,10 +107,10 @@ static void bench_width(const Ctx& c, const std::string& op) {
     } else if (op == "packB" || op == "for_packB") {
         const unsigned gridB = unsigned((c.n_blocks * 32 + kThreads - 1) / kThreads);
         if (op == "packB") {
-            float ms = time_ms(c, [&] { pack_warp_kernel<T, W, POP_PLAIN><<<gridB, kThreads, 0, c.s>>>(c.out, c.in, c.n_blocks, nullptr, T(0)); });
+            float ms = time_ms(c, [&] { pack_warp_kernel<T, W, POP_PLAIN><<<gridB, kThreads, 0, c.s>>>(c.out, c.in, c.n_blocks, nullptr, T(0), nullptr); });
             report("packB", TB, W, c.n_blocks, 128 * (W + TB), ms);
         } else {
-            float ms = time_ms(c, [&] { pack_warp_kernel<T, W, POP_FOR><<<gridB, kThreads, 0, c.s>>>(c.out, c.in, c.n_blocks, nullptr, T(12345)); });
+            float ms = time_ms(c, [&] { pack_warp_kernel<T, W, POP_FOR><<<gridB, kThreads, 0, c.s>>>(c.out, c.in, c.n_blocks, nullptr, T(12345), nullptr); });
             report("for_packB", TB, W, c.n_blocks, 128 * (W + TB), ms);
         }
     } else if (op == "pack") {

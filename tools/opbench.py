@@ -29,6 +29,7 @@ def timeit(fn, iters=7):
 
 
 def main():
+    only = set(sys.argv[1].split(",")) if len(sys.argv) > 1 else None  # e.g. "transpose,untranspose"
     lg_bytes = 32  # 4 GiB unpacked per type
     rows = []
     sp = torch.cuda.current_stream().cuda_stream
@@ -44,6 +45,8 @@ def main():
         widths = sorted({1, tb // 4, tb // 2 + 1, tb - 3, tb})
 
         def rec(op, w, bytes_per_block, fn):
+            if only and op not in only:
+                return
             st = fn()
             assert st == 0, (op, tb, w, st)
             ms = timeit(fn)
@@ -51,7 +54,7 @@ def main():
                          "GBps": round(n * bytes_per_block / (ms * 1e-3) / 1e9, 1),
                          "Gints": round(n * 1024 / (ms * 1e-3) / 1e9, 1)})
             r = rows[-1]
-            print(f"{op:14s} u{tb:<2d} W={w:<2d} {r['us']:9.1f} us {r['GBps']:8.1f} GB/s {r['Gints']:8.1f} Gint/s", flush=True)
+            print(f"{op:26s} u{tb:<2d} W={w:<2d} {r['us']:9.1f} us {r['GBps']:8.1f} GB/s {r['Gints']:8.1f} Gint/s", flush=True)
 
         for w in widths:
             rec("unpack", w, 128 * (w + tb), lambda: _lib.fn("fl_unpack", tb)(w, n, P, U, sp))
@@ -59,10 +62,15 @@ def main():
             rec("unfor_pack", w, 128 * (w + tb), lambda: _lib.fn("fl_unfor_pack", tb)(w, n, P, 12345 % (1 << tb), U, sp))
             rec("for_pack", w, 128 * (w + tb), lambda: _lib.fn("fl_for_pack", tb)(w, n, U, 12345 % (1 << tb), P, sp))
             rec("undelta_pack", w, 128 * (w + tb + 1), lambda: _lib.fn("fl_undelta_pack", tb)(w, n, P, B, U, sp))
+            if tb >= 32:  # fused chains: same algorithmic bytes as undelta_pack / pack + bases
+                rec("undelta_pack_untranspose", w, 128 * (w + tb + 1), lambda: _lib.fn("fl_undelta_pack_untranspose", tb)(w, n, P, B, U, sp))
+                rec("transpose_delta_pack", w, 128 * (w + tb + 1), lambda: _lib.fn("fl_transpose_delta_pack", tb)(w, n, U, B, P, sp))
         rec("delta", 0, 128 * (2 * tb + 1), lambda: _lib.fn("fl_delta", tb)(n, U, B, P, sp))
         rec("undelta", 0, 128 * (2 * tb + 1), lambda: _lib.fn("fl_undelta", tb)(n, U, B, P, sp))
         rec("transpose", 0, 256 * tb, lambda: _lib.fn("fl_transpose", tb)(n, U, P, sp))
         rec("untranspose", 0, 256 * tb, lambda: _lib.fn("fl_untranspose", tb)(n, U, P, sp))
+        if only and "unpack_gather" not in only:
+            continue
         # batched unpack_single: 2^24 random queries
         nq = 1 << 24
         gi = torch.randint(0, n * 1024, (nq,), dtype=torch.int64, device="cuda")
