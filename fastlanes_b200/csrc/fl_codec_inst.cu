@@ -30,7 +30,13 @@ template <class T, int W, int OP>
 static cudaError_t do_unpack(const LaunchArgs& a) {
     // warp-block layout: one warp per 1024-value block (see fl_kernels.cuh)
     const unsigned grid = unsigned((a.n_blocks * 32 + kThreads - 1) / kThreads);
-    unpack_warp_kernel<T, W, OP><<<grid, kThreads, 0, a.stream>>>(
+    size_t smem = 0;
+    if constexpr (OP == UOP_DELTA_ORIG) {  // one block staged per warp
+        smem = size_t(kThreads / 32) * 128 * Lay<T>::TB;
+        static const cudaError_t attr = cudaFuncSetAttribute(unpack_warp_kernel<T, W, OP>, cudaFuncAttributeMaxDynamicSharedMemorySize, int(smem));
+        if (attr != cudaSuccess) return attr;
+    }
+    unpack_warp_kernel<T, W, OP><<<grid, kThreads, smem, a.stream>>>(
         static_cast<const char*>(a.in), static_cast<char*>(a.out), a.n_blocks, static_cast<const T*>(a.refs),
         T(a.ref_scalar), static_cast<const char*>(a.base));
     return cudaGetLastError();
@@ -67,7 +73,13 @@ cudaError_t launch_unpack<elem_t>(int op, const LaunchArgs& a) {
 template <class T, int W, int OP>
 static cudaError_t do_pack(const LaunchArgs& a) {
     const unsigned grid = unsigned((a.n_blocks * 32 + kThreads - 1) / kThreads);  // warp-block layout
-    pack_warp_kernel<T, W, OP><<<grid, kThreads, 0, a.stream>>>(
+    size_t smem = 0;
+    if constexpr (OP == POP_ORIG_DELTA) {  // one block staged per warp
+        smem = size_t(kThreads / 32) * 128 * Lay<T>::TB;
+        static const cudaError_t attr = cudaFuncSetAttribute(pack_warp_kernel<T, W, OP>, cudaFuncAttributeMaxDynamicSharedMemorySize, int(smem));
+        if (attr != cudaSuccess) return attr;
+    }
+    pack_warp_kernel<T, W, OP><<<grid, kThreads, smem, a.stream>>>(
         static_cast<const char*>(a.in), static_cast<char*>(a.out), a.n_blocks, static_cast<const T*>(a.refs),
         T(a.ref_scalar), static_cast<const char*>(a.base));
     return cudaGetLastError();

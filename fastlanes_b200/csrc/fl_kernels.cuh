@@ -191,6 +191,17 @@ __device__ __forceinline__ void scatter_rows_chunk(Slice<T> (&v)[RPG], int r, in
     }
 }
 
+// The fused original-order ops stage one block per warp in shared memory (warp-private tile, __syncwarp only):
+// the register tile is scattered/gathered at its ORIGINAL byte offset A with 16-byte accesses, the global side
+// is a linear 512-bytes-per-instruction copy.  XOR swizzle of the 16-byte bank group (A bits 4..6) with the
+// address bits that vary across a quarter-warp in the scatter (u32: lane bits at A[7], A[10..11]; u64: A[10..12])
+// makes BOTH sides bank-conflict free.
+template <class T>
+__device__ __forceinline__ int orig_tile_swizzle(int A) {
+    if constexpr (sizeof(T) == 4) return A ^ ((((A >> 7) & 1) | (((A >> 10) & 3) << 1)) << 4);
+    else return A ^ (((A >> 10) & 7) << 4);
+}
+
 template <class R>
 __device__ __forceinline__ R shfl_reg(R v, int src) {
     if constexpr (sizeof(R) == 8) return R(__shfl_sync(0xffffffffu, (unsigned long long)v, src));
@@ -302,12 +313,21 @@ unpack_warp_kernel(const char* __restrict__ packed, char* __restrict__ out, size
         // untranspose fused into the store (transpose.rs:18-22): per lane, the RPG rows are RPG consecutive
         // originals -> RPG*sizeof(T)/16 contiguous 16-byte chunks; the row->chunk regrouping is register renaming.
         constexpr int EPC = 16 / int(sizeof(T));
-        char* ob = out + blk * (size_t(128) * TB);
+        extern __shared__ __align__(16) unsigned char orig_tile_smem[];
+        unsigned char* tile = orig_tile_smem + (threadIdx.x >> 5) * (128 * TB);
 #pragma unroll
         for (int r = 0; r < NR; ++r) {
-            char* po = ob + orig_run_byte_offset<T>(q, j, r);
+            const int A0 = orig_run_byte_offset<T>(q, j, r);
 #pragma unroll
-            for (int m = 0; m < RPG / EPC; ++m) stg128_stream(po + m * 16, gather_rows_chunk<T, RPG>(v, r, m));
+            for (int m = 0; m < RPG / EPC; ++m)
+                *reinterpret_cast<uint4*>(tile + orig_tile_swizzle<T>(A0 + m * 16)) = gather_rows_chunk<T, RPG>(v, r, m);
+        }
+        __syncwarp();
+        char* ob = out + blk * (size_t(128) * TB);
+#pragma unroll
+        for (int i = 0; i < (128 * TB) / 512; ++i) {
+            const int A = i * 512 + lane * 16;
+            stg128_stream(ob + A, *reinterpret_cast<const uint4*>(tile + orig_tile_swizzle<T>(A)));
         }
         return;
     }
@@ -356,12 +376,21 @@ pack_warp_kernel(const char* __restrict__ in, char* __restrict__ packed, size_t 
     if constexpr (OP == POP_ORIG_DELTA) {
         // transpose fused into the load (transpose.rs:11-15), then delta along rows (delta.rs:24-33)
         constexpr int EPC = 16 / int(sizeof(T));
+        extern __shared__ __align__(16) unsigned char orig_tile_smem[];
+        unsigned char* tile = orig_tile_smem + (threadIdx.x >> 5) * (128 * TB);
         const char* ib = in + blk * (size_t(128) * TB);
 #pragma unroll
-        for (int r = 0; r < NR; ++r) {
-            const char* pi = ib + orig_run_byte_offset<T>(q, j, r);
+        for (int i = 0; i < (128 * TB) / 512; ++i) {
+            const int A = i * 512 + lane * 16;
+            *reinterpret_cast<uint4*>(tile + orig_tile_swizzle<T>(A)) = ldg128_stream(ib + A);
+        }
+        __syncwarp();
 #pragma unroll
-            for (int m = 0; m < RPG / EPC; ++m) scatter_rows_chunk<T, RPG>(src, r, m, ldg128_stream(pi + m * 16));
+        for (int r = 0; r < NR; ++r) {
+            const int A0 = orig_run_byte_offset<T>(q, j, r);
+#pragma unroll
+            for (int m = 0; m < RPG / EPC; ++m)
+                scatter_rows_chunk<T, RPG>(src, r, m, *reinterpret_cast<const uint4*>(tile + orig_tile_swizzle<T>(A0 + m * 16)));
         }
         const Slice<T> b0 = load_slice<T>(base + blk * 128 + j * 16);  // base[lane]
         const int srcl = WL::group_of_rank(q > 0 ? q - 1 : 0) * 8 + j;
