@@ -304,13 +304,13 @@ class Delta:
     @staticmethod
     def undelta_pack_untranspose(width: int, input, base, output) -> None:
         """untranspose(undelta_pack::<W>(input, base)) in one pass: decode straight to ORIGINAL value order
-        (src/delta.rs:99 then src/transpose.rs:18-22).  u32/u64."""
+        (src/delta.rs:99 then src/transpose.rs:18-22)."""
         i, b, o, dev, n = Delta._three(input, base, output, packed_width=width)
         _call("fl_undelta_pack_untranspose", o.tbits, dev, width, n, i.ptr, b.ptr, o.ptr)
 
     @staticmethod
     def transpose_delta_pack(width: int, input, base, output) -> None:
-        """pack::<W>(delta(transpose(input), base)) in one pass: the encode chain of src/delta.rs:88-95.  u32/u64."""
+        """pack::<W>(delta(transpose(input), base)) in one pass: the encode chain of src/delta.rs:88-95."""
         i, b, o = _Arg(input, "input"), _Arg(base, "base"), _Arg(output, "output")
         dev = _same_space(i, b, o)
         _check_width(width, i.tbits)

@@ -64,8 +64,6 @@ fl_status device_op(Op op, unsigned width, size_t n_blocks, const void* in, void
                     const void* refs, uint64_t ref_scalar, cudaStream_t stream) {
     constexpr unsigned TB = sizeof(T) * 8;
     if (op_has_width(op) && width > TB) return fail(FL_ERR_WIDTH, "width exceeds the bit size of the element type");
-    if ((op == Op::UndeltaPackUntranspose || op == Op::TransposeDeltaPack) && sizeof(T) < 4)
-        return fail(FL_ERR_UNSUPPORTED, "fused original-order ops are implemented for u32/u64");
     if (!op_has_width(op)) width = 0;
     if (n_blocks == 0) return FL_OK;
     if (n_blocks > (size_t(1) << 40)) return fail(FL_ERR_LEN, "n_blocks too large");
@@ -145,8 +143,6 @@ fl_status host_op(Op op, unsigned width, size_t n_blocks, const void* in, void* 
                   uint64_t ref_scalar) {
     constexpr unsigned TB = sizeof(T) * 8;
     if (op_has_width(op) && width > TB) return fail(FL_ERR_WIDTH, "width exceeds the bit size of the element type");
-    if ((op == Op::UndeltaPackUntranspose || op == Op::TransposeDeltaPack) && sizeof(T) < 4)
-        return fail(FL_ERR_UNSUPPORTED, "fused original-order ops are implemented for u32/u64");
     if (!op_has_width(op)) width = 0;
     if (n_blocks == 0) return FL_OK;
     const size_t ib = in_block_bytes(op, TB, width), ob = out_block_bytes(op, TB, width);

@@ -45,15 +45,11 @@ template <class T, int OP, int... W>
 static constexpr std::array<launch_fn, sizeof...(W)> unpack_table(std::integer_sequence<int, W...>) {
     return {{&do_unpack<T, W, OP>...}};
 }
-// fused undelta_pack + untranspose: u32/u64 only this round (dependent context so that `if constexpr` discards)
+// fused undelta_pack + untranspose (all four types)
 template <class T>
 static cudaError_t unpack_delta_orig(const LaunchArgs& a) {
-    if constexpr (sizeof(T) >= 4) {
-        static constexpr auto tab = unpack_table<T, UOP_DELTA_ORIG>(std::make_integer_sequence<int, Lay<T>::TB + 1>{});
-        return tab[a.width](a);
-    } else {
-        return cudaErrorNotSupported;
-    }
+    static constexpr auto tab = unpack_table<T, UOP_DELTA_ORIG>(std::make_integer_sequence<int, Lay<T>::TB + 1>{});
+    return tab[a.width](a);
 }
 template <>
 cudaError_t launch_unpack<elem_t>(int op, const LaunchArgs& a) {
@@ -88,15 +84,11 @@ template <class T, int OP, int... W>
 static constexpr std::array<launch_fn, sizeof...(W)> pack_table(std::integer_sequence<int, W...>) {
     return {{&do_pack<T, W, OP>...}};
 }
-// fused transpose + delta + pack: u32/u64 only this round
+// fused transpose + delta + pack (all four types)
 template <class T>
 static cudaError_t pack_orig_delta(const LaunchArgs& a) {
-    if constexpr (sizeof(T) >= 4) {
-        static constexpr auto tab = pack_table<T, POP_ORIG_DELTA>(std::make_integer_sequence<int, Lay<T>::TB + 1>{});
-        return tab[a.width](a);
-    } else {
-        return cudaErrorNotSupported;
-    }
+    static constexpr auto tab = pack_table<T, POP_ORIG_DELTA>(std::make_integer_sequence<int, Lay<T>::TB + 1>{});
+    return tab[a.width](a);
 }
 template <>
 cudaError_t launch_pack<elem_t>(int op, const LaunchArgs& a) {

@@ -148,6 +148,11 @@ __device__ __forceinline__ typename Lay<T>::R lane_funnel_rt(typename Lay<T>::R 
     }
 }
 
+// Order in which a thread visits its RPG local rows for global loads/stores: address-sequential.
+// u32 (RPG 8) and u8/u16 are already sequential in i; u64 (RPG 16) alternates the two 8-row halves: 0,8,1,9,...
+template <int RPG>
+__host__ __device__ constexpr int warp_visit_row(int ii) { return (RPG == 16) ? ((ii & 1) * 8 + (ii >> 1)) : ii; }
+
 // byte offset of local row i of the run of rank q (global row r = q*RPG + i), see row_byte_offset()
 template <class T, int I>
 __device__ __forceinline__ int warp_row_offset(int q) {
@@ -166,9 +171,8 @@ __device__ __forceinline__ int warp_row_offset(int q) {
 // the RPG rows a thread holds for one lane are RPG consecutive originals.  Byte offset of that run inside the
 // block, for SWAR register r of slice j in the run of rank q (u32/u64 only: one lane per register):
 template <class T>
-__device__ __forceinline__ int orig_run_byte_offset(int q, int j, int r) {
-    static_assert(sizeof(T) >= 4, "original-order fused ops are implemented for u32/u64");
-    const int l = Lay<T>::NR * j + r;
+__device__ __forceinline__ int orig_run_byte_offset(int q, int j, int k) {
+    const int l = (16 / int(sizeof(T))) * j + k;  // lane index: thread j owns lanes [16/S * j, 16/S * (j+1))
     return (64 * (l & 15) + 8 * fl_order_rt(l >> 4) + q * WarpLay<T>::RPG) * int(sizeof(T));
 }
 // chunk m (16 bytes = EPC consecutive rows) of lane-register r out of the row-major register tile v[row].r[r]
@@ -199,7 +203,78 @@ __device__ __forceinline__ void scatter_rows_chunk(Slice<T> (&v)[RPG], int r, in
 template <class T>
 __device__ __forceinline__ int orig_tile_swizzle(int A) {
     if constexpr (sizeof(T) == 4) return A ^ ((((A >> 7) & 1) | (((A >> 10) & 3) << 1)) << 4);
-    else return A ^ (((A >> 10) & 7) << 4);
+    else if constexpr (sizeof(T) == 8) return A ^ (((A >> 10) & 7) << 4);
+    else return A;  // u8/u16 scatter 2-/8-byte pieces: no 16-byte bank-group structure to fix
+}
+
+// register tile v[row].r[..]  ->  warp-private shared tile in ORIGINAL order (this thread's lanes, its run of rows)
+template <class T, int RPG>
+__device__ __forceinline__ void orig_tile_scatter(unsigned char* tile, const Slice<T> (&v)[RPG], int q, int j) {
+    constexpr int NR = Lay<T>::NR;
+    if constexpr (sizeof(T) >= 4) {
+        constexpr int EPC = 16 / int(sizeof(T));
+#pragma unroll
+        for (int r = 0; r < NR; ++r) {
+            const int A0 = orig_run_byte_offset<T>(q, j, r);
+#pragma unroll
+            for (int m = 0; m < RPG / EPC; ++m)
+                *reinterpret_cast<uint4*>(tile + orig_tile_swizzle<T>(A0 + m * 16)) = gather_rows_chunk<T, RPG>(v, r, m);
+        }
+    } else if constexpr (sizeof(T) == 2) {
+        // RPG = 4 rows x 8 lanes: per lane 4 consecutive u16 = 8 bytes
+#pragma unroll
+        for (int k = 0; k < 8; ++k) {
+            const uint32_t sel = (k & 1) ? 0x7632u : 0x5410u;
+            uint2 p;
+            p.x = __byte_perm(v[0].r[k >> 1], v[1].r[k >> 1], sel);
+            p.y = __byte_perm(v[2].r[k >> 1], v[3].r[k >> 1], sel);
+            *reinterpret_cast<uint2*>(tile + orig_run_byte_offset<T>(q, j, k)) = p;
+        }
+    } else {
+        // RPG = 2 rows x 16 lanes: per lane 2 consecutive u8 = 2 bytes
+#pragma unroll
+        for (int k = 0; k < 16; ++k) {
+            const uint32_t b = k & 3;
+            const uint32_t p = __byte_perm(v[0].r[k >> 2], v[1].r[k >> 2], ((4u + b) << 4) | b);
+            *reinterpret_cast<uint16_t*>(tile + orig_run_byte_offset<T>(q, j, k)) = uint16_t(p);
+        }
+    }
+}
+// inverse: shared tile in ORIGINAL order -> register tile
+template <class T, int RPG>
+__device__ __forceinline__ void orig_tile_gather(const unsigned char* tile, Slice<T> (&v)[RPG], int q, int j) {
+    constexpr int NR = Lay<T>::NR;
+    if constexpr (sizeof(T) >= 4) {
+        constexpr int EPC = 16 / int(sizeof(T));
+#pragma unroll
+        for (int r = 0; r < NR; ++r) {
+            const int A0 = orig_run_byte_offset<T>(q, j, r);
+#pragma unroll
+            for (int m = 0; m < RPG / EPC; ++m)
+                scatter_rows_chunk<T, RPG>(v, r, m, *reinterpret_cast<const uint4*>(tile + orig_tile_swizzle<T>(A0 + m * 16)));
+        }
+    } else if constexpr (sizeof(T) == 2) {
+#pragma unroll
+        for (int rr = 0; rr < 4; ++rr) {
+            const uint2 a = *reinterpret_cast<const uint2*>(tile + orig_run_byte_offset<T>(q, j, 2 * rr));
+            const uint2 b = *reinterpret_cast<const uint2*>(tile + orig_run_byte_offset<T>(q, j, 2 * rr + 1));
+            v[0].r[rr] = __byte_perm(a.x, b.x, 0x5410u);
+            v[1].r[rr] = __byte_perm(a.x, b.x, 0x7632u);
+            v[2].r[rr] = __byte_perm(a.y, b.y, 0x5410u);
+            v[3].r[rr] = __byte_perm(a.y, b.y, 0x7632u);
+        }
+    } else {
+#pragma unroll
+        for (int rr = 0; rr < 4; ++rr) {
+            uint32_t p[4];
+#pragma unroll
+            for (int x = 0; x < 4; ++x) p[x] = *reinterpret_cast<const uint16_t*>(tile + orig_run_byte_offset<T>(q, j, 4 * rr + x));
+            const uint32_t t01 = __byte_perm(p[0], p[1], 0x5140u);  // (p0.row0, p1.row0, p0.row1, p1.row1)
+            const uint32_t t23 = __byte_perm(p[2], p[3], 0x5140u);
+            v[0].r[rr] = __byte_perm(t01, t23, 0x5410u);
+            v[1].r[rr] = __byte_perm(t01, t23, 0x7632u);
+        }
+    }
 }
 
 template <class R>
@@ -312,16 +387,9 @@ unpack_warp_kernel(const char* __restrict__ packed, char* __restrict__ out, size
     if constexpr (OP == UOP_DELTA_ORIG) {
         // untranspose fused into the store (transpose.rs:18-22): per lane, the RPG rows are RPG consecutive
         // originals -> RPG*sizeof(T)/16 contiguous 16-byte chunks; the row->chunk regrouping is register renaming.
-        constexpr int EPC = 16 / int(sizeof(T));
         extern __shared__ __align__(16) unsigned char orig_tile_smem[];
         unsigned char* tile = orig_tile_smem + (threadIdx.x >> 5) * (128 * TB);
-#pragma unroll
-        for (int r = 0; r < NR; ++r) {
-            const int A0 = orig_run_byte_offset<T>(q, j, r);
-#pragma unroll
-            for (int m = 0; m < RPG / EPC; ++m)
-                *reinterpret_cast<uint4*>(tile + orig_tile_swizzle<T>(A0 + m * 16)) = gather_rows_chunk<T, RPG>(v, r, m);
-        }
+        orig_tile_scatter<T, RPG>(tile, v, q, j);
         __syncwarp();
         char* ob = out + blk * (size_t(128) * TB);
 #pragma unroll
@@ -332,7 +400,8 @@ unpack_warp_kernel(const char* __restrict__ packed, char* __restrict__ out, size
         return;
     }
     seq_rows<RPG>([&](auto ic) {
-        constexpr int i = decltype(ic)::value;
+        // u64 (RPG = 16): visit local rows as 0,8,1,9,... so that consecutive warp stores are address-sequential
+        constexpr int i = warp_visit_row<RPG>(decltype(ic)::value);
         // global row r = q*RPG + i: offset (FL_ORDER[r/8]*16 + (r%8)*128)*sizeof(T)  (macros.rs:20-24)
         int off;
         if constexpr (RPG >= 8) {
@@ -375,7 +444,6 @@ pack_warp_kernel(const char* __restrict__ in, char* __restrict__ packed, size_t 
     Slice<T> src[RPG];
     if constexpr (OP == POP_ORIG_DELTA) {
         // transpose fused into the load (transpose.rs:11-15), then delta along rows (delta.rs:24-33)
-        constexpr int EPC = 16 / int(sizeof(T));
         extern __shared__ __align__(16) unsigned char orig_tile_smem[];
         unsigned char* tile = orig_tile_smem + (threadIdx.x >> 5) * (128 * TB);
         const char* ib = in + blk * (size_t(128) * TB);
@@ -385,13 +453,7 @@ pack_warp_kernel(const char* __restrict__ in, char* __restrict__ packed, size_t 
             *reinterpret_cast<uint4*>(tile + orig_tile_swizzle<T>(A)) = ldg128_stream(ib + A);
         }
         __syncwarp();
-#pragma unroll
-        for (int r = 0; r < NR; ++r) {
-            const int A0 = orig_run_byte_offset<T>(q, j, r);
-#pragma unroll
-            for (int m = 0; m < RPG / EPC; ++m)
-                scatter_rows_chunk<T, RPG>(src, r, m, *reinterpret_cast<const uint4*>(tile + orig_tile_swizzle<T>(A0 + m * 16)));
-        }
+        orig_tile_gather<T, RPG>(tile, src, q, j);
         const Slice<T> b0 = load_slice<T>(base + blk * 128 + j * 16);  // base[lane]
         const int srcl = WL::group_of_rank(q > 0 ? q - 1 : 0) * 8 + j;
         Slice<T> first_prev;
@@ -405,7 +467,7 @@ pack_warp_kernel(const char* __restrict__ in, char* __restrict__ packed, size_t 
         src[0] = slice_sub<T>(src[0], first_prev);
     } else {
         seq_rows<RPG>([&](auto ic) {
-            constexpr int i = decltype(ic)::value;
+            constexpr int i = warp_visit_row<RPG>(decltype(ic)::value);
             src[i] = load_slice<T>(ip + warp_row_offset<T, i>(q));
         });
     }
@@ -505,7 +567,7 @@ delta_warp_kernel(const char* __restrict__ in, const char* __restrict__ base, ch
     char* op = out + blk * (size_t(128) * TB) + j * 16;
     Slice<T> v[RPG];
     seq_rows<RPG>([&](auto ic) {
-        constexpr int i = decltype(ic)::value;
+        constexpr int i = warp_visit_row<RPG>(decltype(ic)::value);
         v[i] = load_slice<T>(ip + warp_row_offset<T, i>(q));
     });
     Slice<T> carry = load_slice<T>(base + blk * 128 + j * 16);  // delta.rs:26 / :38: prev = base[lane]
@@ -537,7 +599,7 @@ delta_warp_kernel(const char* __restrict__ in, const char* __restrict__ base, ch
         v[0] = slice_sub<T>(v[0], first_prev);
     }
     seq_rows<RPG>([&](auto ic) {
-        constexpr int i = decltype(ic)::value;
+        constexpr int i = warp_visit_row<RPG>(decltype(ic)::value);
         store_slice<T>(op + warp_row_offset<T, i>(q), v[i]);
     });
 }

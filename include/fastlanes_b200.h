@@ -49,7 +49,7 @@ enum {
     FL_ERR_ALIGN = 4, /* device pointer not 16-byte aligned */
     FL_ERR_CUDA = 5,  /* CUDA runtime error or no device; see fl_last_error_string() */
     FL_ERR_NULL = 6,  /* required pointer is NULL */
-    FL_ERR_UNSUPPORTED = 7 /* operation not implemented for this element type (fused original-order ops: u32/u64 only) */
+    FL_ERR_UNSUPPORTED = 7 /* operation not implemented for this element type (reserved; unused in this release) */
 };
 
 /* Library / context -------------------------------------------------------------------------- */
@@ -106,13 +106,13 @@ FL_API fl_status fl_shutdown(void);
                                     void* stream);                                                                  \
     FL_API fl_status fl_host_undelta_pack_##SFX(unsigned width, size_t n_blocks, const T* packed, const T* base, T* out);  \
     /* FUSED decode to ORIGINAL order: untranspose(undelta_pack(packed, base)) in one pass — the decode chain of   \
-     * src/delta.rs:99 + src/transpose.rs:18-22.  u32/u64; u8/u16 -> FL_ERR_UNSUPPORTED. */ \
+     * src/delta.rs:99 + src/transpose.rs:18-22.                                          */ \
     FL_API fl_status fl_undelta_pack_untranspose_##SFX(unsigned width, size_t n_blocks, const T* packed, const T* base,    \
                                                 T* out, void* stream);                                              \
     FL_API fl_status fl_host_undelta_pack_untranspose_##SFX(unsigned width, size_t n_blocks, const T* packed,              \
                                                      const T* base, T* out);                                        \
     /* FUSED encode from ORIGINAL order: pack(delta(transpose(in), base)) in one pass — the encode chain of        \
-     * src/delta.rs:88-95.  u32/u64; u8/u16 -> FL_ERR_UNSUPPORTED. */                                               \
+     * src/delta.rs:88-95.                                                                                      */ \
     FL_API fl_status fl_transpose_delta_pack_##SFX(unsigned width, size_t n_blocks, const T* in, const T* base, T* packed, \
                                             void* stream);                                                          \
     FL_API fl_status fl_host_transpose_delta_pack_##SFX(unsigned width, size_t n_blocks, const T* in, const T* base,       \

@@ -41,6 +41,8 @@ template <class T> struct Abi;
         static fl_status delta(size_t n, const T* i, const T* b, T* o) { return fl_host_delta_##SFX(n, i, b, o); } \
         static fl_status undelta(size_t n, const T* i, const T* b, T* o) { return fl_host_undelta_##SFX(n, i, b, o); } \
         static fl_status undelta_pack(unsigned w, size_t n, const T* i, const T* b, T* o) { return fl_host_undelta_pack_##SFX(w, n, i, b, o); } \
+        static fl_status undelta_pack_untranspose(unsigned w, size_t n, const T* i, const T* b, T* o) { return fl_host_undelta_pack_untranspose_##SFX(w, n, i, b, o); } \
+        static fl_status transpose_delta_pack(unsigned w, size_t n, const T* i, const T* b, T* o) { return fl_host_transpose_delta_pack_##SFX(w, n, i, b, o); } \
         static fl_status transpose(size_t n, const T* i, T* o) { return fl_host_transpose_##SFX(n, i, o); }     \
         static fl_status untranspose(size_t n, const T* i, T* o) { return fl_host_untranspose_##SFX(n, i, o); } \
     };
@@ -121,6 +123,17 @@ struct Delta {
     template <std::size_t W>
     static void undelta_pack(const Packed<T, W>& input, const Base& base, std::array<T, 1024>& output) {
         detail::check(detail::Abi<T>::undelta_pack(W, 1, input.data(), base.data(), output.data()), "undelta_pack");
+    }
+    // Fused chains (compositions of the reference methods, one GPU pass; u32/u64):
+    //   untranspose(undelta_pack::<W>(input, base))  — src/delta.rs:99 + src/transpose.rs:18-22
+    template <std::size_t W>
+    static void undelta_pack_untranspose(const Packed<T, W>& input, const Base& base, std::array<T, 1024>& output) {
+        detail::check(detail::Abi<T>::undelta_pack_untranspose(W, 1, input.data(), base.data(), output.data()), "undelta_pack_untranspose");
+    }
+    //   pack::<W>(delta(transpose(input), base))      — src/delta.rs:88-95
+    template <std::size_t W>
+    static void transpose_delta_pack(const std::array<T, 1024>& input, const Base& base, Packed<T, W>& output) {
+        detail::check(detail::Abi<T>::transpose_delta_pack(W, 1, input.data(), base.data(), output.data()), "transpose_delta_pack");
     }
 };
 

@@ -62,6 +62,20 @@ int main() {
         EXPECT(transposed == undelta);
         for (std::size_t i = 0; i < 1024; ++i) EXPECT(transposed[i] == values[transpose(i)]);
     }
+    {   // fused chains == compositions (u32): encode from original order, decode back to original order
+        constexpr std::size_t W = 12;
+        std::array<uint32_t, 1024> values{}, transposed{}, deltas{}, decoded{};
+        for (std::size_t i = 0; i < 1024; ++i) values[i] = uint32_t(i * 3 + 5);
+        Delta<uint32_t>::Base base{};
+        Packed<uint32_t, W> fused{}, chained{};
+        Delta<uint32_t>::transpose_delta_pack<W>(values, base, fused);
+        Transpose<uint32_t>::transpose(values, transposed);
+        Delta<uint32_t>::delta(transposed, base, deltas);
+        BitPacking<uint32_t>::pack<W>(deltas, chained);
+        EXPECT(fused == chained);
+        Delta<uint32_t>::undelta_pack_untranspose<W>(fused, base, decoded);
+        EXPECT(decoded == values);
+    }
     {   // test_ffor
         constexpr std::size_t W = 15;
         std::array<uint16_t, 1024> values{}, unpacked{};

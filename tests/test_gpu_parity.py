@@ -158,7 +158,7 @@ def test_error_behaviour(fl):
     assert b"" != _lib.lib().fl_last_error_string()
 
 
-@pytest.mark.parametrize("tb", [32, 64])
+@pytest.mark.parametrize("tb", [8, 16, 32, 64])
 def test_fused_original_order_chains(fl, oracle, tb):
     """decode straight to original order / encode straight from it, against the oracle's
     composition of the reference methods (src/delta.rs:88-99, src/transpose.rs:11-22)."""
@@ -178,6 +178,8 @@ def test_fused_original_order_chains(fl, oracle, tb):
         assert np.array_equal(to_host(p, tb), expect_p), (tb, w, "transpose_delta_pack")
     # the README-style pipeline: encode then decode returns the input when deltas fit the width
     w = tb // 2
+    if tb < 32:
+        return
     values = (np.arange(n * 1024, dtype=np.uint64) * 3 + 7).astype(DT[tb])
     zero_base = np.zeros(n * (1024 // tb), dtype=DT[tb])
     p = dev_empty(n * 1024 * w // tb, tb)
@@ -187,10 +189,3 @@ def test_fused_original_order_chains(fl, oracle, tb):
     # per-block: values restart, so the first delta of each lane is the value itself; only check it round-trips
     # when every delta (incl. the first, relative to base 0) fits in w bits: true for block 0 of u32/u64 here
     assert np.array_equal(to_host(back, tb)[:1024], values[:1024])
-
-
-def test_fused_original_order_unsupported_types(fl):
-    v = dev_empty(1024, 16)
-    with pytest.raises(fl.FastLanesError) as e:
-        fl.Delta.undelta_pack_untranspose(5, dev_empty(320, 16), dev_empty(64, 16), v)
-    assert e.value.status == 7

@@ -62,7 +62,7 @@ def main():
             rec("unfor_pack", w, 128 * (w + tb), lambda: _lib.fn("fl_unfor_pack", tb)(w, n, P, 12345 % (1 << tb), U, sp))
             rec("for_pack", w, 128 * (w + tb), lambda: _lib.fn("fl_for_pack", tb)(w, n, U, 12345 % (1 << tb), P, sp))
             rec("undelta_pack", w, 128 * (w + tb + 1), lambda: _lib.fn("fl_undelta_pack", tb)(w, n, P, B, U, sp))
-            if tb >= 32:  # fused chains: same algorithmic bytes as undelta_pack / pack + bases
+            if True:  # fused chains: same algorithmic bytes as undelta_pack / pack + bases
                 rec("undelta_pack_untranspose", w, 128 * (w + tb + 1), lambda: _lib.fn("fl_undelta_pack_untranspose", tb)(w, n, P, B, U, sp))
                 rec("transpose_delta_pack", w, 128 * (w + tb + 1), lambda: _lib.fn("fl_transpose_delta_pack", tb)(w, n, U, B, P, sp))
         rec("delta", 0, 128 * (2 * tb + 1), lambda: _lib.fn("fl_delta", tb)(n, U, B, P, sp))
