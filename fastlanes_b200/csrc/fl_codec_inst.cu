@@ -28,6 +28,15 @@ static inline unsigned grid_for(size_t n_blocks) {
 #if FLB_PART == 0
 template <class T, int W, int OP>
 static cudaError_t do_unpack(const LaunchArgs& a) {
+    if constexpr (sizeof(T) == 1 && OP == UOP_DELTA && W < 8) {
+        // u8 fused delta at W < 8: a 1 KiB block gives a warp too little work to amortise the 4-group shuffle
+        // scan (ALU-bound, 5.1-6.1 TB/s); the row-slice kernel keeps the whole 8-row chain in one thread
+        // (6.3-6.5 TB/s measured, profiles/kbench_r01_u8_u16_delta.txt).
+        unpack_kernel<T, W, OP><<<grid_for(a.n_blocks), kThreads, 0, a.stream>>>(
+            static_cast<const char*>(a.in), static_cast<char*>(a.out), a.n_blocks, static_cast<const T*>(a.refs),
+            T(a.ref_scalar), static_cast<const char*>(a.base));
+        return cudaGetLastError();
+    }
     // warp-block layout: one warp per 1024-value block (see fl_kernels.cuh)
     const unsigned grid = unsigned((a.n_blocks * 32 + kThreads - 1) / kThreads);
     size_t smem = 0;

@@ -140,6 +140,8 @@ __device__ __forceinline__ typename Lay<T>::R lane_add(typename Lay<T>::R a, typ
     using R = typename Lay<T>::R;
     if constexpr (Lay<T>::LPR == 1) {
         return a + b;
+    } else if constexpr (Lay<T>::LPR == 2) {
+        return __vadd2(a, b);  // sm_100a: one VIADD.16x2
     } else {
         constexpr R H = rep_value<T>(T(T(1) << (Lay<T>::TB - 1)));
         return ((a & ~H) + (b & ~H)) ^ ((a ^ b) & H);
@@ -150,6 +152,8 @@ __device__ __forceinline__ typename Lay<T>::R lane_sub(typename Lay<T>::R a, typ
     using R = typename Lay<T>::R;
     if constexpr (Lay<T>::LPR == 1) {
         return a - b;
+    } else if constexpr (Lay<T>::LPR == 2) {
+        return __vsub2(a, b);  // sm_100a: one VIADD.16x2 with a negated operand
     } else {
         constexpr R H = rep_value<T>(T(T(1) << (Lay<T>::TB - 1)));
         return ((a | H) - (b & ~H)) ^ ((a ^ ~b) & H);
