@@ -4,6 +4,7 @@
 // Host family:   chunked H2D -> kernel -> D2H pipeline over internal streams (per-device context).
 // There is no CPU compute path anywhere in this library: every value is produced by a CUDA kernel.
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include <mutex>
 #include <string>
@@ -59,6 +60,17 @@ inline size_t out_block_bytes(Op op, unsigned tbits, unsigned width) {
     return op_output_packed(op) ? size_t(128) * width : size_t(128) * tbits;
 }
 
+// Two transpose implementations are built: the CTA-tile kernel (fl_misc.cu) and the warp-block kernel
+// (fl_kernels.cuh).  FLB_TRANSPOSE=tile|warp selects one for A/B measurement; the default is the measured best.
+inline int transpose_variant() {
+    static const int v = [] {
+        const char* e = std::getenv("FLB_TRANSPOSE");
+        if (e && std::strcmp(e, "tile") == 0) return 0;
+        return 1;
+    }();
+    return v;
+}
+
 template <class T>
 fl_status device_op(Op op, unsigned width, size_t n_blocks, const void* in, void* out, const void* base,
                     const void* refs, uint64_t ref_scalar, cudaStream_t stream) {
@@ -89,8 +101,8 @@ fl_status device_op(Op op, unsigned width, size_t n_blocks, const void* in, void
         case Op::TransposeDeltaPack: e = flb::launch_pack<T>(flb::kPackOrigDelta, a); break;
         case Op::Delta: e = flb::launch_delta<T>(false, a); break;
         case Op::Undelta: e = flb::launch_delta<T>(true, a); break;
-        case Op::Transpose: e = flb::launch_transpose<T>(false, a); break;
-        case Op::Untranspose: e = flb::launch_transpose<T>(true, a); break;
+        case Op::Transpose: e = transpose_variant() ? flb::launch_transpose_warp<T>(false, a) : flb::launch_transpose<T>(false, a); break;
+        case Op::Untranspose: e = transpose_variant() ? flb::launch_transpose_warp<T>(true, a) : flb::launch_transpose<T>(true, a); break;
     }
     if (e != cudaSuccess) return cuda_fail(e, "kernel launch");
     return FL_OK;

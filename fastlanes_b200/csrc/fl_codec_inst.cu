@@ -120,6 +120,20 @@ cudaError_t launch_delta<elem_t>(bool undo, const LaunchArgs& a) {
     else delta_warp_kernel<elem_t, false><<<grid, kThreads, 0, a.stream>>>(in, base, out, a.n_blocks);
     return cudaGetLastError();
 }
+
+template <class T, bool UNDO>
+static cudaError_t do_transpose_warp(const LaunchArgs& a) {
+    const unsigned grid = unsigned((a.n_blocks * 32 + kThreads - 1) / kThreads);
+    const size_t smem = size_t(kThreads / 32) * 128 * Lay<T>::TB;
+    static const cudaError_t attr = cudaFuncSetAttribute(transpose_warp_kernel<T, UNDO>, cudaFuncAttributeMaxDynamicSharedMemorySize, int(smem));
+    if (attr != cudaSuccess) return attr;
+    transpose_warp_kernel<T, UNDO><<<grid, kThreads, smem, a.stream>>>(static_cast<const char*>(a.in), static_cast<char*>(a.out), a.n_blocks);
+    return cudaGetLastError();
+}
+template <>
+cudaError_t launch_transpose_warp<elem_t>(bool undo, const LaunchArgs& a) {
+    return undo ? do_transpose_warp<elem_t, true>(a) : do_transpose_warp<elem_t, false>(a);
+}
 #endif
 
 }  // namespace flb

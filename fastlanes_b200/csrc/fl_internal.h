@@ -25,6 +25,7 @@ enum : int { kPackPlain = 0, kPackFor = 1, kPackOrigDelta = 2 };
 template <class T> cudaError_t launch_unpack(int op, const LaunchArgs& a);
 template <class T> cudaError_t launch_pack(int op, const LaunchArgs& a);
 template <class T> cudaError_t launch_delta(bool undo, const LaunchArgs& a);
+template <class T> cudaError_t launch_transpose_warp(bool undo, const LaunchArgs& a);
 
 // Defined for all types in fl_misc.cu.
 template <class T> cudaError_t launch_transpose(bool undo, const LaunchArgs& a);

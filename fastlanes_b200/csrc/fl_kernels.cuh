@@ -605,6 +605,56 @@ delta_warp_kernel(const char* __restrict__ in, const char* __restrict__ base, ch
 }
 
 // ---------------------------------------------------------------------------------------------------
+// a14 Transpose::transpose / untranspose (src/transpose.rs:11-22), warp-block layout: the same machinery as the
+// fused original-order chains without the codec in between.  One warp = one block; the ORIGINAL-order side is a
+// linear 512-bytes-per-instruction copy through the warp-private swizzled tile, the TRANSPOSED-order side is the
+// row-major register tile (rows of the transposed vector are exactly the unpacked rows, macros.rs:20-24).
+// ---------------------------------------------------------------------------------------------------
+template <class T, bool UNDO>
+__global__ void __launch_bounds__(kThreads)
+transpose_warp_kernel(const char* __restrict__ in, char* __restrict__ out, size_t n_blocks) {
+    using WL = WarpLay<T>;
+    constexpr int TB = Lay<T>::TB;
+    constexpr int RPG = WL::RPG;
+    const size_t blk = (size_t(blockIdx.x) * kThreads + threadIdx.x) >> 5;
+    if (blk >= n_blocks) return;
+    const int lane = threadIdx.x & 31;
+    const int g = lane >> 3, j = lane & 7;
+    const int q = WL::rank_of_group(g);
+    extern __shared__ __align__(16) unsigned char orig_tile_smem[];
+    unsigned char* tile = orig_tile_smem + (threadIdx.x >> 5) * (128 * TB);
+    const char* ib = in + blk * (size_t(128) * TB);
+    char* ob = out + blk * (size_t(128) * TB);
+    Slice<T> v[RPG];
+    if constexpr (!UNDO) {
+        // transposed[i] = original[t(i)]: original -> tile (linear) -> register rows -> transposed rows
+#pragma unroll
+        for (int i = 0; i < (128 * TB) / 512; ++i) {
+            const int A = i * 512 + lane * 16;
+            *reinterpret_cast<uint4*>(tile + orig_tile_swizzle<T>(A)) = ldg128_stream(ib + A);
+        }
+        __syncwarp();
+        orig_tile_gather<T, RPG>(tile, v, q, j);
+        seq_rows<RPG>([&](auto ic) {
+            constexpr int i = warp_visit_row<RPG>(decltype(ic)::value);
+            store_slice<T>(ob + j * 16 + warp_row_offset<T, i>(q), v[i]);
+        });
+    } else {
+        seq_rows<RPG>([&](auto ic) {
+            constexpr int i = warp_visit_row<RPG>(decltype(ic)::value);
+            v[i] = load_slice<T>(ib + j * 16 + warp_row_offset<T, i>(q));
+        });
+        orig_tile_scatter<T, RPG>(tile, v, q, j);
+        __syncwarp();
+#pragma unroll
+        for (int i = 0; i < (128 * TB) / 512; ++i) {
+            const int A = i * 512 + lane * 16;
+            stg128_stream(ob + A, *reinterpret_cast<const uint4*>(tile + orig_tile_swizzle<T>(A)));
+        }
+    }
+}
+
+// ---------------------------------------------------------------------------------------------------
 // pack family:  a7 BitPacking::pack (src/bitpacking.rs:65-74), a18 FoR::for_pack (src/ffor.rs:24-36).
 //   in : n_blocks x (128*T bytes)        packed : n_blocks x (128*W bytes)
 // ---------------------------------------------------------------------------------------------------

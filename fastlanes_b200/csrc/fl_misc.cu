@@ -9,75 +9,17 @@ namespace flb {
 //   transposed[i] = original[t(i)],  t(i) = (i%16)*64 + FL_ORDER[(i/16)%8]*8 + i/128   (:29-36)
 // Writing i = a + 16 b + 128 c and o = t(i) = 64 a + 8 FL_ORDER[b] + c the permutation is the axis
 // reversal [a:16][f:8][c:8] -> [c:8][b:8][a:16] with b = FL_ORDER[f] (FL_ORDER is an involution,
-// src/lib.rs:53-59).  One CTA stages kTrBlocks blocks in shared memory with coalesced 16-byte global
-// accesses on both sides; the gather (transpose) / scatter (untranspose) happens on shared memory at
-// element granularity.  Shared rows of 64 originals are padded by one 16-byte unit to spread banks.
+// src/lib.rs:53-59).
 // ---------------------------------------------------------------------------------------------------
 constexpr int kTrThreads = 256;
-
-template <class T>
-struct TrCfg {
-    static constexpr int EPC = 16 / int(sizeof(T));        // elements per 16-byte chunk
-    static constexpr int CHUNKS = 1024 / EPC;               // 16-byte chunks per block
-    static constexpr int ROW_ELEMS = 64 + EPC;              // padded shared row (64 originals + 1 chunk)
-    static constexpr int SMEM_ELEMS = 16 * ROW_ELEMS;       // per block
-    static constexpr int BLOCKS_PER_CTA = (sizeof(T) == 8) ? 2 : (sizeof(T) == 4 ? 4 : 8);
-};
 
 __device__ __forceinline__ int transpose_index(int i) {
     return (i % 16) * 64 + fl_order((i / 16) % 8) * 8 + i / 128;  // transpose.rs:31-35
 }
-// position of original element o inside the padded shared tile
-template <class T>
-__device__ __forceinline__ int smem_pos(int o) {
-    return (o >> 6) * TrCfg<T>::ROW_ELEMS + (o & 63);
-}
-
-template <class T, bool UNDO>
-__global__ void __launch_bounds__(kTrThreads)
-transpose_kernel(const T* __restrict__ in, T* __restrict__ out, size_t n_blocks) {
-    using C = TrCfg<T>;
-    __shared__ __align__(16) T tile[C::BLOCKS_PER_CTA][C::SMEM_ELEMS];
-    const size_t blk0 = size_t(blockIdx.x) * C::BLOCKS_PER_CTA;
-    const int nb = int(min(size_t(C::BLOCKS_PER_CTA), n_blocks - blk0));
-
-    // Phase 1: coalesced 16-byte loads.  The tile always holds the ORIGINAL-order side:
-    //   transpose:   tile[o] = in[o]          (linear fill)
-    //   untranspose: tile[t(i)] = in[i]       (element scatter while filling)
-    for (int c = threadIdx.x; c < nb * C::CHUNKS; c += kTrThreads) {
-        const int b = c / C::CHUNKS, q = c % C::CHUNKS;
-        const uint4 v = ldg128_stream(reinterpret_cast<const char*>(in + (blk0 + b) * 1024) + q * 16);
-        alignas(16) T e[C::EPC];
-        *reinterpret_cast<uint4*>(e) = v;
-        if constexpr (!UNDO) {
-            // 64 % EPC == 0, so a chunk never crosses a padded row: one 16-byte shared store
-            *reinterpret_cast<uint4*>(&tile[b][smem_pos<T>(q * C::EPC)]) = v;
-        } else {
-#pragma unroll
-            for (int k = 0; k < C::EPC; ++k) tile[b][smem_pos<T>(transpose_index(q * C::EPC + k))] = e[k];
-        }
-    }
-    __syncthreads();
-    // Phase 2: coalesced 16-byte stores.
-    //   transpose:   out[i] = tile[t(i)]      (element gather)
-    //   untranspose: out[o] = tile[o]         (linear drain)
-    for (int c = threadIdx.x; c < nb * C::CHUNKS; c += kTrThreads) {
-        const int b = c / C::CHUNKS, q = c % C::CHUNKS;
-        uint4 v;
-        if constexpr (!UNDO) {
-            alignas(16) T e[C::EPC];
-#pragma unroll
-            for (int k = 0; k < C::EPC; ++k) e[k] = tile[b][smem_pos<T>(transpose_index(q * C::EPC + k))];
-            v = *reinterpret_cast<uint4*>(e);
-        } else {
-            v = *reinterpret_cast<const uint4*>(&tile[b][smem_pos<T>(q * C::EPC)]);
-        }
-        stg128_stream(reinterpret_cast<char*>(out + (blk0 + b) * 1024) + q * 16, v);
-    }
-}
 
 // ---------------------------------------------------------------------------------------------------
-// u32 / u64 fast path: 16-byte-chunk tiles, zero shared-memory bank conflicts, no per-element traffic.
+// CTA-tile variant: 16-byte-chunk tiles, zero shared-memory bank conflicts, no per-element traffic.
+// (Selected with FLB_TRANSPOSE=tile; the default is transpose_warp_kernel in fl_kernels.cuh, which measured faster.)
 // A thread owns the square tile  {EPC consecutive a} x {the EPC elements of one original chunk}  (EPC = 16/sizeof(T)):
 // it moves EPC original chunks <-> EPC transposed chunks and the EPC x EPC element transpose between them is a
 // pure register renaming.  The original-order side lives in shared memory with an XOR swizzle on the chunk
@@ -189,17 +131,10 @@ template <class T>
 cudaError_t launch_transpose(bool undo, const LaunchArgs& a) {
     const T* in = static_cast<const T*>(a.in);
     T* out = static_cast<T*>(a.out);
-    if constexpr (sizeof(T) >= 1) {
-        using TC = TileCfg<T>;
-        const unsigned grid = unsigned((a.n_blocks + TC::BLOCKS - 1) / TC::BLOCKS);
-        if (undo) transpose_tile_kernel<T, true><<<grid, kTrThreads, 0, a.stream>>>(in, out, a.n_blocks);
-        else transpose_tile_kernel<T, false><<<grid, kTrThreads, 0, a.stream>>>(in, out, a.n_blocks);
-        return cudaGetLastError();
-    }
-    using C = TrCfg<T>;
-    const unsigned grid = unsigned((a.n_blocks + C::BLOCKS_PER_CTA - 1) / C::BLOCKS_PER_CTA);
-    if (undo) transpose_kernel<T, true><<<grid, kTrThreads, 0, a.stream>>>(in, out, a.n_blocks);
-    else transpose_kernel<T, false><<<grid, kTrThreads, 0, a.stream>>>(in, out, a.n_blocks);
+    using TC = TileCfg<T>;
+    const unsigned grid = unsigned((a.n_blocks + TC::BLOCKS - 1) / TC::BLOCKS);
+    if (undo) transpose_tile_kernel<T, true><<<grid, kTrThreads, 0, a.stream>>>(in, out, a.n_blocks);
+    else transpose_tile_kernel<T, false><<<grid, kTrThreads, 0, a.stream>>>(in, out, a.n_blocks);
     return cudaGetLastError();
 }
 
