@@ -265,6 +265,24 @@ class FoR:
             _call("fl_unfor_pack", o.tbits, dev, width, n, i.ptr, _ref_value(reference, o.tbits), o.ptr)
 
 
+    @staticmethod
+    def block_minmax(input, mins, maxs) -> None:
+        """Per-block min and max (not in the reference: the statistics its callers compute before `for_pack`,
+        which takes `reference` and W as givens, src/ffor.rs:5-10).  mins/maxs: one element per block."""
+        i, lo, hi = _Arg(input, "input"), _Arg(mins, "mins"), _Arg(maxs, "maxs")
+        dev = _same_space(i, lo, hi)
+        n = _n_blocks_unpacked(i, "Input")
+        _expect(lo, n, "Mins")
+        _expect(hi, n, "Maxs")
+        _call("fl_block_minmax", i.tbits, dev, n, i.ptr, lo.ptr, hi.ptr)
+
+    @staticmethod
+    def choose(mins, maxs, tbits: int):
+        """Host helper: (reference per block, one width for the batch) = (mins, bits(max over blocks of max - min))."""
+        span = (np.asarray(maxs).astype(np.uint64) - np.asarray(mins).astype(np.uint64)) & np.uint64((1 << tbits) - 1 if tbits < 64 else 0xFFFFFFFFFFFFFFFF)
+        return mins, int(span.max()).bit_length() if span.size else 0
+
+
 class Delta:
     """src/delta.rs:6-17.  `base` holds LANES = 1024/T elements per block."""
 

@@ -199,6 +199,56 @@ fl_status host_op(Op op, unsigned width, size_t n_blocks, const void* in, void* 
 }
 
 template <class T>
+fl_status device_minmax(size_t n_blocks, const T* in, T* mins, T* maxs, cudaStream_t stream) {
+    if (n_blocks == 0) return FL_OK;
+    if (!in || !mins || !maxs) return fail(FL_ERR_NULL, "null pointer");
+    if (!aligned16(in)) return fail(FL_ERR_ALIGN, "device pointers must be 16-byte aligned");
+    cudaError_t e = flb::launch_block_minmax<T>(n_blocks, in, mins, maxs, stream);
+    if (e != cudaSuccess) return cuda_fail(e, "minmax launch");
+    return FL_OK;
+}
+
+template <class T>
+fl_status host_minmax(size_t n_blocks, const T* in, T* mins, T* maxs) {
+    if (n_blocks == 0) return FL_OK;
+    if (!in || !mins || !maxs) return fail(FL_ERR_NULL, "null pointer");
+    HostCtx* ctx = nullptr;
+    if (fl_status s = get_ctx(&ctx)) return s;
+    std::lock_guard<std::mutex> lk(ctx->mu);
+    const size_t chunk = g_chunk_blocks ? g_chunk_blocks : 16384;
+    const size_t n_slots = size_t(g_n_streams > 0 ? g_n_streams : 3);
+    if (ctx->slots.size() < n_slots) ctx->slots.resize(n_slots);
+    const size_t n_chunks = (n_blocks + chunk - 1) / chunk;
+    const size_t use_slots = n_chunks < n_slots ? n_chunks : n_slots;
+    const size_t cb = n_blocks < chunk ? n_blocks : chunk;
+    const size_t half = (cb * sizeof(T) + 15) & ~size_t(15);
+    for (size_t s = 0; s < use_slots; ++s) {
+        Slot& sl = ctx->slots[s];
+        if (!sl.stream) FL_CUDA(cudaStreamCreateWithFlags(&sl.stream, cudaStreamNonBlocking));
+        if (fl_status st = ensure(&sl.d_in, &sl.in_cap, cb * 1024 * sizeof(T))) return st;
+        if (fl_status st = ensure(&sl.d_out, &sl.out_cap, 2 * half)) return st;
+    }
+    fl_status result = FL_OK;
+    for (size_t c = 0; c < n_chunks && result == FL_OK; ++c) {
+        Slot& sl = ctx->slots[c % use_slots];
+        const size_t b0 = c * chunk;
+        const size_t nb = (n_blocks - b0) < chunk ? (n_blocks - b0) : chunk;
+        T* d_min = static_cast<T*>(sl.d_out);
+        T* d_max = reinterpret_cast<T*>(static_cast<char*>(sl.d_out) + half);
+        FL_CUDA(cudaMemcpyAsync(sl.d_in, in + b0 * 1024, nb * 1024 * sizeof(T), cudaMemcpyHostToDevice, sl.stream));
+        result = device_minmax<T>(nb, static_cast<const T*>(sl.d_in), d_min, d_max, sl.stream);
+        if (result != FL_OK) break;
+        FL_CUDA(cudaMemcpyAsync(mins + b0, d_min, nb * sizeof(T), cudaMemcpyDeviceToHost, sl.stream));
+        FL_CUDA(cudaMemcpyAsync(maxs + b0, d_max, nb * sizeof(T), cudaMemcpyDeviceToHost, sl.stream));
+    }
+    for (size_t s = 0; s < use_slots; ++s) {
+        cudaError_t e = cudaStreamSynchronize(ctx->slots[s].stream);
+        if (e != cudaSuccess && result == FL_OK) result = cuda_fail(e, "cudaStreamSynchronize");
+    }
+    return result;
+}
+
+template <class T>
 fl_status device_gather(unsigned width, size_t n_blocks, const T* packed, const uint64_t* gidx, size_t n, T* out,
                         int* oob_flag, cudaStream_t stream) {
     if (width > sizeof(T) * 8) return fail(FL_ERR_WIDTH, "width exceeds the bit size of the element type");
@@ -388,6 +438,12 @@ fl_status fl_shutdown(void) {
     }                                                                                                                   \
     fl_status fl_host_transpose_delta_pack_##SFX(unsigned width, size_t n, const T* in, const T* base, T* packed) {     \
         return host_op<T>(Op::TransposeDeltaPack, width, n, in, packed, base, 0);                                       \
+    }                                                                                                                   \
+    fl_status fl_block_minmax_##SFX(size_t n, const T* in, T* mins, T* maxs, void* st) {                                \
+        return device_minmax<T>(n, in, mins, maxs, (cudaStream_t)st);                                                   \
+    }                                                                                                                   \
+    fl_status fl_host_block_minmax_##SFX(size_t n, const T* in, T* mins, T* maxs) {                                     \
+        return host_minmax<T>(n, in, mins, maxs);                                                                       \
     }                                                                                                                   \
     fl_status fl_transpose_##SFX(size_t n, const T* in, T* out, void* st) {                                             \
         return device_op<T>(Op::Transpose, 0, n, in, out, nullptr, nullptr, 0, (cudaStream_t)st);                       \

@@ -33,4 +33,7 @@ template <class T>
 cudaError_t launch_gather(unsigned width, size_t n_blocks, const T* packed, const uint64_t* global_index, size_t n,
                           T* out, int* oob_flag, cudaStream_t stream);
 
+template <class T>
+cudaError_t launch_block_minmax(size_t n_blocks, const T* in, T* mins, T* maxs, cudaStream_t stream);
+
 }  // namespace flb

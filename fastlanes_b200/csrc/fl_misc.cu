@@ -139,6 +139,87 @@ cudaError_t launch_transpose(bool undo, const LaunchArgs& a) {
 }
 
 // ---------------------------------------------------------------------------------------------------
+// Per-block min / max: the statistics a caller needs before FoR::for_pack
+// (src/ffor.rs:24-36 takes `reference` and W as givens): reference = min, W = bits(max - min).
+// One warp = one block, linear 512-bytes-per-instruction reads, SWAR lane-wise min/max (u16: VIMNMX.U16x2),
+// then a butterfly over the warp.  Read-only: 128*T bytes per block.
+// ---------------------------------------------------------------------------------------------------
+template <class T> struct MinMax;
+template <> struct MinMax<uint8_t> {
+    __device__ static uint32_t mn(uint32_t a, uint32_t b) { return __vminu4(a, b); }
+    __device__ static uint32_t mx(uint32_t a, uint32_t b) { return __vmaxu4(a, b); }
+};
+template <> struct MinMax<uint16_t> {
+    __device__ static uint32_t mn(uint32_t a, uint32_t b) { return __vminu2(a, b); }
+    __device__ static uint32_t mx(uint32_t a, uint32_t b) { return __vmaxu2(a, b); }
+};
+template <> struct MinMax<uint32_t> {
+    __device__ static uint32_t mn(uint32_t a, uint32_t b) { return min(a, b); }
+    __device__ static uint32_t mx(uint32_t a, uint32_t b) { return max(a, b); }
+};
+template <> struct MinMax<uint64_t> {
+    __device__ static uint64_t mn(uint64_t a, uint64_t b) { return min(a, b); }
+    __device__ static uint64_t mx(uint64_t a, uint64_t b) { return max(a, b); }
+};
+
+template <class T>
+__global__ void __launch_bounds__(256)
+block_minmax_kernel(const char* __restrict__ in, T* __restrict__ mins, T* __restrict__ maxs, size_t n_blocks) {
+    using R = typename Lay<T>::R;
+    using M = MinMax<T>;
+    constexpr int TB = Lay<T>::TB;
+    constexpr int NR = Lay<T>::NR;
+    const size_t blk = (size_t(blockIdx.x) * 256 + threadIdx.x) >> 5;
+    if (blk >= n_blocks) return;
+    const int lane = threadIdx.x & 31;
+    const char* ib = in + blk * (size_t(128) * TB) + lane * 16;
+    Slice<T> lo, hi;
+    {
+        const Slice<T> v = load_slice<T>(ib);
+        lo = v; hi = v;
+    }
+#pragma unroll
+    for (int i = 1; i < (128 * TB) / 512; ++i) {
+        const Slice<T> v = load_slice<T>(ib + i * 512);
+#pragma unroll
+        for (int r = 0; r < NR; ++r) { lo.r[r] = M::mn(lo.r[r], v.r[r]); hi.r[r] = M::mx(hi.r[r], v.r[r]); }
+    }
+    R l = lo.r[0], h = hi.r[0];
+#pragma unroll
+    for (int r = 1; r < NR; ++r) { l = M::mn(l, lo.r[r]); h = M::mx(h, hi.r[r]); }
+#pragma unroll
+    for (int d = 16; d >= 1; d >>= 1) {
+        R ol, oh;
+        if constexpr (sizeof(R) == 8) {
+            ol = __shfl_xor_sync(0xffffffffu, (unsigned long long)l, d); oh = __shfl_xor_sync(0xffffffffu, (unsigned long long)h, d);
+        } else {
+            ol = __shfl_xor_sync(0xffffffffu, l, d); oh = __shfl_xor_sync(0xffffffffu, h, d);
+        }
+        l = M::mn(l, ol); h = M::mx(h, oh);
+    }
+    if (lane == 0) {
+        T tl, th;
+        if constexpr (sizeof(T) == 1) {
+            uint32_t a = M::mn(l, l >> 16); a = M::mn(a, a >> 8); tl = T(a & 0xFF);
+            uint32_t b = M::mx(h, h >> 16); b = M::mx(b, b >> 8); th = T(b & 0xFF);
+        } else if constexpr (sizeof(T) == 2) {
+            tl = T(M::mn(l, l >> 16) & 0xFFFF); th = T(M::mx(h, h >> 16) & 0xFFFF);
+        } else {
+            tl = T(l); th = T(h);
+        }
+        mins[blk] = tl; maxs[blk] = th;
+    }
+}
+
+template <class T>
+cudaError_t launch_block_minmax(size_t n_blocks, const T* in, T* mins, T* maxs, cudaStream_t stream) {
+    if (n_blocks == 0) return cudaSuccess;
+    const unsigned grid = unsigned((n_blocks * 32 + 255) / 256);
+    block_minmax_kernel<T><<<grid, 256, 0, stream>>>(reinterpret_cast<const char*>(in), mins, maxs, n_blocks);
+    return cudaGetLastError();
+}
+
+// ---------------------------------------------------------------------------------------------------
 // Batched BitPacking::unpack_single (src/bitpacking.rs:132-179): one thread per query, runtime width.
 // (lane,row) follow lanes_by_index / rows_by_index (:207-232) in closed form instead of the 1 KiB tables.
 // ---------------------------------------------------------------------------------------------------
@@ -197,7 +278,8 @@ cudaError_t launch_gather(unsigned width, size_t n_blocks, const T* packed, cons
 #define FLB_INST(T)                                                                                          \
     template cudaError_t launch_transpose<T>(bool, const LaunchArgs&);                                       \
     template cudaError_t launch_gather<T>(unsigned, size_t, const T*, const uint64_t*, size_t, T*, int*,     \
-                                          cudaStream_t);
+                                          cudaStream_t);                                                    \
+    template cudaError_t launch_block_minmax<T>(size_t, const T*, T*, T*, cudaStream_t);
 FLB_INST(uint8_t)
 FLB_INST(uint16_t)
 FLB_INST(uint32_t)

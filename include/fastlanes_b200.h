@@ -117,6 +117,11 @@ FL_API fl_status fl_shutdown(void);
                                             void* stream);                                                          \
     FL_API fl_status fl_host_transpose_delta_pack_##SFX(unsigned width, size_t n_blocks, const T* in, const T* base,       \
                                                  T* packed);                                                        \
+    /* Per-block min and max: what a caller needs to pick FoR's `reference` (= min) and W (= bits(max - min))      \
+     * before FoR::for_pack, which takes both as givens (src/ffor.rs:5-10).  SURVEY.md §8f rank 3.  mins/maxs:      \
+     * n_blocks elements each. */                                                                                   \
+    FL_API fl_status fl_block_minmax_##SFX(size_t n_blocks, const T* in, T* mins, T* maxs, void* stream);                  \
+    FL_API fl_status fl_host_block_minmax_##SFX(size_t n_blocks, const T* in, T* mins, T* maxs);                           \
     /* Transpose::transpose / untranspose — src/transpose.rs:5-6 (impl :11-22) */                                   \
     FL_API fl_status fl_transpose_##SFX(size_t n_blocks, const T* in, T* out, void* stream);                               \
     FL_API fl_status fl_untranspose_##SFX(size_t n_blocks, const T* in, T* out, void* stream);                             \

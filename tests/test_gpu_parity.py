@@ -189,3 +189,32 @@ def test_fused_original_order_chains(fl, oracle, tb):
     # per-block: values restart, so the first delta of each lane is the value itself; only check it round-trips
     # when every delta (incl. the first, relative to base 0) fits in w bits: true for block 0 of u32/u64 here
     assert np.array_equal(to_host(back, tb)[:1024], values[:1024])
+
+
+@pytest.mark.parametrize("tb", [8, 16, 32, 64])
+def test_block_minmax_and_for_pipeline(fl, oracle, tb):
+    """per-block statistics -> reference / width -> for_pack_refs -> unfor_pack_refs round trip."""
+    import torch
+
+    rng = np.random.default_rng(800 + tb)
+    n = 133
+    span_bits = tb // 2 - 1
+    lo = rand_bytes(rng, n * (tb // 8), tb) >> DT[tb](1)                      # per-block offsets (no overflow)
+    values = (np.repeat(lo, 1024) + (rand_bytes(rng, n * 128 * tb, tb) & DT[tb](mask(span_bits)))).astype(DT[tb])
+    d_values = to_dev(values)
+    d_min, d_max = dev_empty(n, tb), dev_empty(n, tb)
+    fl.FoR.block_minmax(d_values, d_min, d_max)
+    v2 = values.reshape(n, 1024)
+    assert np.array_equal(to_host(d_min, tb), v2.min(axis=1))
+    assert np.array_equal(to_host(d_max, tb), v2.max(axis=1))
+    h_min, h_max = np.zeros(n, DT[tb]), np.zeros(n, DT[tb])
+    fl.FoR.block_minmax(values, h_min, h_max)                                 # host family
+    assert np.array_equal(h_min, v2.min(axis=1)) and np.array_equal(h_max, v2.max(axis=1))
+    refs, w = fl.FoR.choose(h_min, h_max, tb)
+    assert w <= span_bits
+    packed = dev_empty(n * 1024 * w // tb, tb)
+    fl.FoR.for_pack(w, d_values, d_min, packed)
+    assert np.array_equal(to_host(packed, tb), oracle.for_pack(values, refs, w))
+    back = dev_empty(n * 1024, tb)
+    fl.FoR.unfor_pack(w, packed, d_min, back)
+    assert torch.equal(back, d_values)

@@ -67,6 +67,8 @@ def main():
                 rec("transpose_delta_pack", w, 128 * (w + tb + 1), lambda: _lib.fn("fl_transpose_delta_pack", tb)(w, n, U, B, P, sp))
         rec("delta", 0, 128 * (2 * tb + 1), lambda: _lib.fn("fl_delta", tb)(n, U, B, P, sp))
         rec("undelta", 0, 128 * (2 * tb + 1), lambda: _lib.fn("fl_undelta", tb)(n, U, B, P, sp))
+        mn = torch.empty(n, dtype=TDT[tb], device="cuda"); mx = torch.empty(n, dtype=TDT[tb], device="cuda")
+        rec("block_minmax", 0, 128 * tb, lambda: _lib.fn("fl_block_minmax", tb)(n, U, mn.data_ptr(), mx.data_ptr(), sp))
         rec("transpose", 0, 256 * tb, lambda: _lib.fn("fl_transpose", tb)(n, U, P, sp))
         rec("untranspose", 0, 256 * tb, lambda: _lib.fn("fl_untranspose", tb)(n, U, P, sp))
         if only and "unpack_gather" not in only:
