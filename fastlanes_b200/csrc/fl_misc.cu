@@ -162,6 +162,8 @@ template <> struct MinMax<uint64_t> {
     __device__ static uint64_t mx(uint64_t a, uint64_t b) { return max(a, b); }
 };
 
+// G threads cooperate on one block (u8: 8, u16: 16, u32/u64: 32) so that every thread reduces >= 8 chunks
+// in registers before the log2(G)-step butterfly; a warp covers 32/G consecutive blocks.
 template <class T>
 __global__ void __launch_bounds__(256)
 block_minmax_kernel(const char* __restrict__ in, T* __restrict__ mins, T* __restrict__ maxs, size_t n_blocks) {
@@ -169,18 +171,17 @@ block_minmax_kernel(const char* __restrict__ in, T* __restrict__ mins, T* __rest
     using M = MinMax<T>;
     constexpr int TB = Lay<T>::TB;
     constexpr int NR = Lay<T>::NR;
-    const size_t blk = (size_t(blockIdx.x) * 256 + threadIdx.x) >> 5;
-    if (blk >= n_blocks) return;
-    const int lane = threadIdx.x & 31;
-    const char* ib = in + blk * (size_t(128) * TB) + lane * 16;
-    Slice<T> lo, hi;
-    {
-        const Slice<T> v = load_slice<T>(ib);
-        lo = v; hi = v;
-    }
+    constexpr int G = (sizeof(T) == 1) ? 8 : (sizeof(T) == 2 ? 16 : 32);
+    constexpr int CHUNKS = (128 * TB) / 16;  // 16-byte chunks per block
+    const size_t tid = size_t(blockIdx.x) * 256 + threadIdx.x;
+    const size_t blk = tid / G;
+    const int t = int(tid % G);
+    const bool active = blk < n_blocks;  // whole groups are active or not; shuffles below stay inside a group
+    const char* ib = in + (active ? blk : 0) * (size_t(128) * TB) + t * 16;
+    Slice<T> lo = load_slice<T>(ib), hi = lo;
 #pragma unroll
-    for (int i = 1; i < (128 * TB) / 512; ++i) {
-        const Slice<T> v = load_slice<T>(ib + i * 512);
+    for (int i = 1; i < CHUNKS / G; ++i) {
+        const Slice<T> v = load_slice<T>(ib + i * (G * 16));
 #pragma unroll
         for (int r = 0; r < NR; ++r) { lo.r[r] = M::mn(lo.r[r], v.r[r]); hi.r[r] = M::mx(hi.r[r], v.r[r]); }
     }
@@ -188,7 +189,7 @@ block_minmax_kernel(const char* __restrict__ in, T* __restrict__ mins, T* __rest
 #pragma unroll
     for (int r = 1; r < NR; ++r) { l = M::mn(l, lo.r[r]); h = M::mx(h, hi.r[r]); }
 #pragma unroll
-    for (int d = 16; d >= 1; d >>= 1) {
+    for (int d = G / 2; d >= 1; d >>= 1) {
         R ol, oh;
         if constexpr (sizeof(R) == 8) {
             ol = __shfl_xor_sync(0xffffffffu, (unsigned long long)l, d); oh = __shfl_xor_sync(0xffffffffu, (unsigned long long)h, d);
@@ -197,7 +198,7 @@ block_minmax_kernel(const char* __restrict__ in, T* __restrict__ mins, T* __rest
         }
         l = M::mn(l, ol); h = M::mx(h, oh);
     }
-    if (lane == 0) {
+    if (active && t == 0) {
         T tl, th;
         if constexpr (sizeof(T) == 1) {
             uint32_t a = M::mn(l, l >> 16); a = M::mn(a, a >> 8); tl = T(a & 0xFF);
@@ -214,7 +215,8 @@ block_minmax_kernel(const char* __restrict__ in, T* __restrict__ mins, T* __rest
 template <class T>
 cudaError_t launch_block_minmax(size_t n_blocks, const T* in, T* mins, T* maxs, cudaStream_t stream) {
     if (n_blocks == 0) return cudaSuccess;
-    const unsigned grid = unsigned((n_blocks * 32 + 255) / 256);
+    constexpr int G = (sizeof(T) == 1) ? 8 : (sizeof(T) == 2 ? 16 : 32);
+    const unsigned grid = unsigned((n_blocks * G + 255) / 256);
     block_minmax_kernel<T><<<grid, 256, 0, stream>>>(reinterpret_cast<const char*>(in), mins, maxs, n_blocks);
     return cudaGetLastError();
 }
