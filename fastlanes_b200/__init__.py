@@ -30,7 +30,7 @@ from ._lib import FastLanesError, LIB_PATH, exported_symbols  # noqa: F401
 FL_ORDER = (0, 4, 2, 6, 1, 5, 3, 7)  # src/lib.rs:22
 
 __all__ = ["BitPacking", "FoR", "Delta", "Transpose", "FastLanes", "FastLanesError", "FL_ORDER",
-           "packed_len", "version", "device_count", "host_configure", "pinned_empty", "shutdown"]
+           "packed_len", "version", "device_count", "init", "host_configure", "pinned_empty", "shutdown"]
 
 
 class FastLanes:
@@ -54,6 +54,11 @@ def version() -> str:
 
 def device_count() -> int:
     return _lib.lib().fl_device_count()
+
+
+def init(device: int = 0) -> None:
+    """Optional warm-up: make `device` current and create the host-path streams (fl_init)."""
+    _lib.check(_lib.lib().fl_init(device))
 
 
 def host_configure(chunk_blocks: int = 0, n_streams: int = 0) -> None:

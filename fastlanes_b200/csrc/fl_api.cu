@@ -316,6 +316,18 @@ int fl_device_count(void) {
     if (cudaGetDeviceCount(&n) != cudaSuccess) { (void)cudaGetLastError(); return 0; }
     return n;
 }
+fl_status fl_init(int device) {
+    FL_CUDA(cudaSetDevice(device));
+    FL_CUDA(cudaFree(nullptr));  // force primary-context creation
+    HostCtx* ctx = nullptr;
+    if (fl_status s = get_ctx(&ctx)) return s;
+    std::lock_guard<std::mutex> lk(ctx->mu);
+    const size_t n_slots = size_t(g_n_streams > 0 ? g_n_streams : 3);
+    if (ctx->slots.size() < n_slots) ctx->slots.resize(n_slots);
+    for (Slot& sl : ctx->slots)
+        if (!sl.stream) FL_CUDA(cudaStreamCreateWithFlags(&sl.stream, cudaStreamNonBlocking));
+    return FL_OK;
+}
 fl_status fl_host_configure(size_t chunk_blocks, int n_streams) {
     std::lock_guard<std::mutex> lk(g_ctx_mu);
     g_chunk_blocks = chunk_blocks ? chunk_blocks : 16384;

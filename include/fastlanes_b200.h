@@ -57,6 +57,9 @@ FL_API const char* fl_version(void);
 FL_API const char* fl_last_error_string(void);       /* thread-local, never NULL */
 FL_API const char* fl_status_string(fl_status s);
 FL_API int fl_device_count(void);                    /* 0 when no usable CUDA device */
+/* Optional: make `device` current for the calling thread and create its host-path context (streams) up front so the
+ * first fl_host_* call does not pay for it.  Every entry point also works without it (contexts are created lazily). */
+FL_API fl_status fl_init(int device);
 /* Host-path tuning for the CURRENT device: blocks per pipelined chunk (0 = default 16384) and
  * number of internal streams (0 = default 3).  Takes effect on the next fl_host_* call. */
 FL_API fl_status fl_host_configure(size_t chunk_blocks, int n_streams);
