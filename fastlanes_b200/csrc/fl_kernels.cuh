@@ -1,10 +1,24 @@
-// fl_kernels.cuh — batched sm_100a kernels of the FastLanes hot path (row-slice layout, see fl_device.cuh).
+// fl_kernels.cuh — batched sm_100a kernels of the FastLanes hot path.
 //
-// One thread = one 16-byte column slice of one block; 8 threads = one block; a warp = 4 consecutive
-// blocks.  No shared memory, no shuffles, no divergence: the serial per-lane chain of the reference
-// (T rows, src/macros.rs:139-170; the T-long prefix-add of src/delta.rs:48-63) is a per-thread register
-// chain, and the 8 x (warps) threads supply the memory-level parallelism.  Every kernel is HBM-bound;
-// algorithmic bytes per block are in DESIGN.md.
+// Two thread mappings over the same per-thread primitives (fl_device.cuh):
+//
+//  * WARP-BLOCK (shipped): one warp = one 1024-value block.  The four 8-thread groups split the T rows into runs of
+//    T/4 consecutive rows; a thread owns the 16-byte column slice j of its group's rows.  Every warp-wide access is
+//    4 x 128 B, contiguous for u32/u64 (512 B), and a block is read/written by a handful of back-to-back
+//    instructions of one warp: measured 6.5-7.2 TB/s on every op (profiles/opbench_r01.txt).  Cross-group
+//    dependencies (the delta prefix chain, packed words straddling two runs) go through warp shuffles; the
+//    original-order variants (fused untranspose / transpose, standalone transposes) stage one block per warp in an
+//    XOR-swizzled shared-memory tile guarded by __syncwarp only.
+//        unpack_warp_kernel, pack_warp_kernel, delta_warp_kernel, transpose_warp_kernel
+//
+//  * ROW-SLICE (first correct path; kept for the A/B measurement in tools/kbench.cu, and used for u8 fused delta at
+//    W < 8 where it is faster): 8 threads = one block, a warp = 4 consecutive blocks; no shared memory, no shuffles:
+//    the serial per-lane chain of the reference (T rows, src/macros.rs:139-170; the prefix-add of
+//    src/delta.rs:48-63) is a per-thread register chain.  5.8-6.2 TB/s: each warp instruction touches four
+//    different blocks and a block takes T instructions to complete, which the DRAM controller likes less.
+//        unpack_kernel, pack_kernel, delta_kernel
+//
+// Every kernel is HBM-bound integer shift/mask/add; algorithmic bytes per block are in DESIGN.md §5.
 #pragma once
 #include <type_traits>
 #include <utility>
