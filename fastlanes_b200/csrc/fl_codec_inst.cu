@@ -42,10 +42,14 @@ static cudaError_t do_unpack(const LaunchArgs& a) {
     size_t smem = 0;
     if constexpr (OP == UOP_DELTA_ORIG) {  // one block staged per warp
         smem = size_t(kThreads / 32) * 128 * Lay<T>::TB;
-        static const cudaError_t attr = cudaFuncSetAttribute(unpack_warp_kernel<T, W, OP>, cudaFuncAttributeMaxDynamicSharedMemorySize, int(smem));
+        static const cudaError_t attr = cudaFuncSetAttribute(unpack_warp_kernel<T, W, OP, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, int(smem));
         if (attr != cudaSuccess) return attr;
     }
-    unpack_warp_kernel<T, W, OP><<<grid, kThreads, smem, a.stream>>>(
+    // TMA bulk load of the packed block (one cp.async.bulk per warp): measured +0.5..8% on u32 (largest at W >= 25,
+    // profiles/kbench_r01_tma_u32.txt).  The original-order variant already owns a dynamic shared tile: keep it direct.
+    // u8 blocks (<= 1 KiB packed) are too small to amortise the mbarrier round trip: measured slower, keep direct.
+    constexpr bool kTma = (OP != UOP_DELTA_ORIG) && sizeof(T) >= 2;
+    unpack_warp_kernel<T, W, OP, kTma><<<grid, kThreads, smem, a.stream>>>(
         static_cast<const char*>(a.in), static_cast<char*>(a.out), a.n_blocks, static_cast<const T*>(a.refs),
         T(a.ref_scalar), static_cast<const char*>(a.base));
     return cudaGetLastError();

@@ -110,6 +110,25 @@ __device__ __forceinline__ void stg128_stream(void* p, uint4 v) {
                  : "memory");
 }
 
+// ---- TMA 1-D bulk copy global -> shared::cta completing on an mbarrier (SASS: UBLKCP + SYNCS) ----------------
+__device__ __forceinline__ unsigned smem_addr(const void* p) { return (unsigned)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void mbar_init(unsigned bar, unsigned count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count) : "memory");
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+}
+__device__ __forceinline__ void mbar_arrive_expect_tx(unsigned bar, unsigned bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_wait_parity(unsigned bar, unsigned parity) {
+    asm volatile(
+        "{\n .reg .pred p;\n FLB_WAIT:\n mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n @p bra FLB_DONE;\n bra FLB_WAIT;\n FLB_DONE:\n}"
+        ::"r"(bar), "r"(parity) : "memory");
+}
+__device__ __forceinline__ void tma_bulk_load(unsigned dst_smem, const void* src_global, unsigned bytes, unsigned bar) {
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+                 ::"r"(dst_smem), "l"(src_global), "r"(bytes), "r"(bar) : "memory");
+}
+
 template <class T>
 __device__ __forceinline__ Slice<T> to_slice(uint4 v) {
     Slice<T> s;

@@ -312,7 +312,10 @@ __device__ __forceinline__ typename Lay<T>::R lane_funnel_left_rt(typename Lay<T
     }
 }
 
-template <class T, int W, int OP>
+// TMA = true: the block's 128*W packed bytes arrive with ONE cp.async.bulk (TMA 1-D bulk copy) per warp into a
+// warp-private shared buffer, completion on a per-warp mbarrier; the word-rows are then read with LDS.128.  Every
+// packed byte crosses L2 exactly once (the direct path re-reads the word-rows that two groups share when W % 4 != 0).
+template <class T, int W, int OP, bool TMA = false>
 __global__ void __launch_bounds__(kThreads)
 unpack_warp_kernel(const char* __restrict__ packed, char* __restrict__ out, size_t n_blocks,
                    const T* __restrict__ refs, T ref_scalar, const char* __restrict__ base) {
@@ -330,6 +333,32 @@ unpack_warp_kernel(const char* __restrict__ packed, char* __restrict__ out, size
     const char* pk = packed + blk * (size_t(128) * W) + j * 16;
     char* o = out + blk * (size_t(128) * TB) + j * 16;
 
+    // word-row k of this block, this thread's 16-byte slice
+    constexpr bool USE_TMA = TMA && W > 0 && (kThreads / 32) * 128 * W + 128 <= 48 * 1024;  // static shared-memory limit (u64: W <= 47)
+    __shared__ __align__(128) unsigned char tma_buf[USE_TMA ? kThreads / 32 : 1][USE_TMA ? 128 * W : 16];
+    __shared__ __align__(8) unsigned long long tma_bar[USE_TMA ? kThreads / 32 : 1];
+    // issue the independent global loads (delta bases) BEFORE waiting on the bulk copy: the mbarrier wait is a
+    // compiler memory barrier, anything after it would be serialised behind the TMA round trip
+    Slice<T> carry = slice_zero<T>();
+    if constexpr (OP == UOP_DELTA || OP == UOP_DELTA_ORIG) carry = load_slice<T>(base + blk * 128 + j * 16);
+    const unsigned char* sp = nullptr;
+    if constexpr (USE_TMA) {
+        const int wi = threadIdx.x >> 5;
+        const unsigned bar = smem_addr(&tma_bar[wi]);
+        if (lane == 0) mbar_init(bar, 1);
+        __syncwarp();
+        if (lane == 0) {
+            mbar_arrive_expect_tx(bar, 128 * W);
+            tma_bulk_load(smem_addr(&tma_buf[wi][0]), packed + blk * (size_t(128) * W), 128 * W, bar);
+        }
+        mbar_wait_parity(bar, 0);
+        sp = &tma_buf[wi][0] + j * 16;
+    }
+    auto load_word_row = [&](unsigned k) -> Slice<T> {
+        if constexpr (USE_TMA) return to_slice<T>(*reinterpret_cast<const uint4*>(sp + k * 128));
+        else return load_slice<T>(pk + k * 128);
+    };
+
     Slice<T> v[RPG];
     if constexpr (W == 0) {
 #pragma unroll
@@ -338,7 +367,7 @@ unpack_warp_kernel(const char* __restrict__ packed, char* __restrict__ out, size
         // macros.rs:126-132: row r is word-row r
         seq_rows<RPG>([&](auto ic) {
             constexpr int i = decltype(ic)::value;
-            v[i] = load_slice<T>(pk + (q * RPG + i) * 128);
+            v[i] = load_word_row(unsigned(q * RPG + i));
         });
     } else {
         constexpr bool ALIGNED = (W % 4) == 0;              // then q*RPG*W is a multiple of T for every q
@@ -350,7 +379,7 @@ unpack_warp_kernel(const char* __restrict__ packed, char* __restrict__ out, size
         seq_rows<NL>([&](auto mc) {
             constexpr int m = decltype(mc)::value;
             const unsigned k = (k0 + m < unsigned(W)) ? k0 + m : unsigned(W - 1);  // clamp: never read past the block
-            w[m] = load_slice<T>(pk + k * 128);
+            w[m] = load_word_row(k);
         });
         Slice<T> a[NA];
         if constexpr (ALIGNED) {
@@ -383,7 +412,6 @@ unpack_warp_kernel(const char* __restrict__ packed, char* __restrict__ out, size
         // delta.rs:56-60: running wrapping sum along rows per lane, seeded with base[lane]
 #pragma unroll
         for (int i = 1; i < RPG; ++i) v[i] = slice_add<T>(v[i], v[i - 1]);
-        Slice<T> carry = load_slice<T>(base + blk * 128 + j * 16);
 #pragma unroll
         for (int qq = 0; qq < 3; ++qq) {  // totals of the runs that precede this one in row order
             const int src = WL::group_of_rank(qq) * 8 + j;

@@ -50,6 +50,22 @@ __global__ void __launch_bounds__(256) read_kernel(const uint4* __restrict__ in,
     }
 }
 
+__global__ void checksum_kernel(const uint4* p, size_t n, unsigned long long* out) {
+    unsigned long long acc = 0;
+    for (size_t i = size_t(blockIdx.x) * blockDim.x + threadIdx.x; i < n; i += size_t(gridDim.x) * blockDim.x) {
+        uint4 v = p[i];
+        acc += (unsigned long long)v.x * 3 + (unsigned long long)v.y * 5 + (unsigned long long)v.z * 7 + (unsigned long long)v.w * 11 + (i & 0xffff);
+    }
+    atomicAdd(out, acc);
+}
+static unsigned long long checksum(const void* p, size_t bytes, cudaStream_t s) {
+    unsigned long long* d; unsigned long long h = 0;
+    CK(cudaMalloc(&d, 8)); CK(cudaMemsetAsync(d, 0, 8, s));
+    checksum_kernel<<<148 * 4, 256, 0, s>>>(static_cast<const uint4*>(p), bytes / 16, d);
+    CK(cudaMemcpyAsync(&h, d, 8, cudaMemcpyDeviceToHost, s)); CK(cudaStreamSynchronize(s)); CK(cudaFree(d));
+    return h;
+}
+
 struct Ctx {
     char* in; char* out; char* base; size_t n_blocks; int iters; cudaStream_t s; cudaEvent_t e0, e1;
 };
@@ -86,9 +102,16 @@ static void bench_width(const Ctx& c, const std::string& op) {
     if (op == "unpack") {
         float ms = time_ms(c, [&] { unpack_kernel<T, W, UOP_PLAIN><<<grid, kThreads, 0, c.s>>>(c.in, c.out, c.n_blocks, nullptr, T(0), nullptr); });
         report("unpack", TB, W, c.n_blocks, 128 * (W + TB), ms);
-    } else if (op == "unpackB" || op == "unfor_packB" || op == "undelta_packB") {
+    } else if (op == "unpackB" || op == "unpackT" || op == "unfor_packB" || op == "undelta_packB") {
         const unsigned gridB = unsigned((c.n_blocks * 32 + kThreads - 1) / kThreads);
-        if (op == "unpackB") {
+        if (op == "unpackT") {
+            float ms = time_ms(c, [&] { unpack_warp_kernel<T, W, UOP_PLAIN, true><<<gridB, kThreads, 0, c.s>>>(c.in, c.out, c.n_blocks, nullptr, T(0), nullptr); });
+            report("unpackT", TB, W, c.n_blocks, 128 * (W + TB), ms);
+            const unsigned long long ct = checksum(c.out, c.n_blocks * 128 * size_t(TB), c.s);
+            unpack_warp_kernel<T, W, UOP_PLAIN><<<gridB, kThreads, 0, c.s>>>(c.in, c.out, c.n_blocks, nullptr, T(0), nullptr);
+            const unsigned long long cb = checksum(c.out, c.n_blocks * 128 * size_t(TB), c.s);
+            if (ct != cb) printf("  !! unpackT checksum MISMATCH at W=%d\n", W);
+        } else if (op == "unpackB") {
             float ms = time_ms(c, [&] { unpack_warp_kernel<T, W, UOP_PLAIN><<<gridB, kThreads, 0, c.s>>>(c.in, c.out, c.n_blocks, nullptr, T(0), nullptr); });
             report("unpackB", TB, W, c.n_blocks, 128 * (W + TB), ms);
         } else if (op == "unfor_packB") {
