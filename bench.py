@@ -401,7 +401,7 @@ def main():
                           "Gints": round(n_blocks * 1024 / (per_w_ms[w] * 1e-3) / 1e9, 1)} for w in WIDTHS}
     worst = min(WIDTHS, key=lambda w: per_width[str(w)]["GBps"])
     roofline = {
-        "bound": "hbm", "kernel": "flb::unpack_warp_kernel<uint32_t, W, UOP_PLAIN> (W=1..32, one launch per width)",
+        "bound": "hbm", "kernel": "flb::unpack_warp_kernel<uint32_t, W, UOP_PLAIN, TMA> (W=1..32, one launch per width)",
         "achieved": round(achieved, 1), "peak": peak, "unit": "GB/s", "frac": round(achieved / peak, 4),
         "peak_source": peak_src, "traffic": None,
         "algorithmic_bytes_per_launch": "128*(W+32) bytes/block * 2^%d blocks" % args.log2_blocks,

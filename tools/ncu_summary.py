@@ -39,7 +39,7 @@ def raw_summary(path):
 
 def main():
     os.makedirs(DST, exist_ok=True)
-    lines = [f"# ncu --set full summaries, round {RND} (kernel: flb::unpack_warp_kernel<uint32_t, W, UOP_PLAIN>, 2^20 blocks)\n",
+    lines = [f"# ncu --set full summaries, round {RND} (kernel: flb::unpack_warp_kernel<uint32_t, W, UOP_PLAIN, TMA>, 2^20 blocks)\n",
              "Captured with `ncu --set full --clock-control none --import-source on` on build/kbench/kb_u32 (one launch after 3 warm-ups).",
              "Durations under ncu are serialised / replayed: use them for traffic and shares, not as bench values.\n"]
     traffic = {}
