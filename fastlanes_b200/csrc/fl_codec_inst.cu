@@ -21,7 +21,7 @@ using elem_t = uint64_t;
 
 using launch_fn = cudaError_t (*)(const LaunchArgs&);
 
-static inline unsigned grid_for(size_t n_blocks) {
+[[maybe_unused]] static inline unsigned grid_for(size_t n_blocks) {
     return unsigned((n_blocks * kSlicesPerBlock + kThreads - 1) / kThreads);
 }
 
@@ -82,13 +82,14 @@ cudaError_t launch_unpack<elem_t>(int op, const LaunchArgs& a) {
 template <class T, int W, int OP>
 static cudaError_t do_pack(const LaunchArgs& a) {
     const unsigned grid = unsigned((a.n_blocks * 32 + kThreads - 1) / kThreads);  // warp-block layout
-    size_t smem = 0;
-    if constexpr (OP == POP_ORIG_DELTA) {  // one block staged per warp
-        smem = size_t(kThreads / 32) * 128 * Lay<T>::TB;
-        static const cudaError_t attr = cudaFuncSetAttribute(pack_warp_kernel<T, W, OP>, cudaFuncAttributeMaxDynamicSharedMemorySize, int(smem));
-        if (attr != cudaSuccess) return attr;
-    }
-    pack_warp_kernel<T, W, OP><<<grid, kThreads, smem, a.stream>>>(
+    // Every variant stages one block per warp in dynamic shared memory: the original-order op as its swizzled tile,
+    // the plain / FoR ops as the landing buffer of the TMA bulk load (+3..7% measured, profiles/kbench_r01_tma_pack_u32.txt).
+    // (u8: a 1 KiB block does not amortise the mbarrier round trip — measured slower — so it keeps direct loads.)
+    constexpr bool kTma = (OP != POP_ORIG_DELTA) && sizeof(T) >= 2;
+    const size_t smem = (kTma || OP == POP_ORIG_DELTA) ? size_t(kThreads / 32) * 128 * Lay<T>::TB + (kTma ? (kThreads / 32) * 8 : 0) : 0;
+    static const cudaError_t attr = cudaFuncSetAttribute(pack_warp_kernel<T, W, OP, kTma>, cudaFuncAttributeMaxDynamicSharedMemorySize, int(smem));
+    if (attr != cudaSuccess) return attr;
+    pack_warp_kernel<T, W, OP, kTma><<<grid, kThreads, smem, a.stream>>>(
         static_cast<const char*>(a.in), static_cast<char*>(a.out), a.n_blocks, static_cast<const T*>(a.refs),
         T(a.ref_scalar), static_cast<const char*>(a.base));
     return cudaGetLastError();

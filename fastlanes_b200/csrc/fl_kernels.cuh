@@ -429,7 +429,7 @@ unpack_warp_kernel(const char* __restrict__ packed, char* __restrict__ out, size
     if constexpr (OP == UOP_DELTA_ORIG) {
         // untranspose fused into the store (transpose.rs:18-22): per lane, the RPG rows are RPG consecutive
         // originals -> RPG*sizeof(T)/16 contiguous 16-byte chunks; the row->chunk regrouping is register renaming.
-        extern __shared__ __align__(16) unsigned char orig_tile_smem[];
+        extern __shared__ __align__(128) unsigned char orig_tile_smem[];
         unsigned char* tile = orig_tile_smem + (threadIdx.x >> 5) * (128 * TB);
         orig_tile_scatter<T, RPG>(tile, v, q, j);
         __syncwarp();
@@ -465,7 +465,8 @@ unpack_warp_kernel(const char* __restrict__ packed, char* __restrict__ out, size
 // that straddle two (or, for W < 4, up to four) groups are OR-merged through warp shuffles: the
 // higher-rank group owns a shared word.
 // ---------------------------------------------------------------------------------------------------
-template <class T, int W, int OP>
+// TMA = true (plain / FoR ops): the 128*T-byte unpacked block arrives with one cp.async.bulk per warp.
+template <class T, int W, int OP, bool TMA = false>
 __global__ void __launch_bounds__(kThreads)
 pack_warp_kernel(const char* __restrict__ in, char* __restrict__ packed, size_t n_blocks,
                  const T* __restrict__ refs, T ref_scalar, const char* __restrict__ base) {
@@ -486,7 +487,7 @@ pack_warp_kernel(const char* __restrict__ in, char* __restrict__ packed, size_t 
     Slice<T> src[RPG];
     if constexpr (OP == POP_ORIG_DELTA) {
         // transpose fused into the load (transpose.rs:11-15), then delta along rows (delta.rs:24-33)
-        extern __shared__ __align__(16) unsigned char orig_tile_smem[];
+        extern __shared__ __align__(128) unsigned char orig_tile_smem[];
         unsigned char* tile = orig_tile_smem + (threadIdx.x >> 5) * (128 * TB);
         const char* ib = in + blk * (size_t(128) * TB);
 #pragma unroll
@@ -508,10 +509,30 @@ pack_warp_kernel(const char* __restrict__ in, char* __restrict__ packed, size_t 
         for (int i = RPG - 1; i >= 1; --i) src[i] = slice_sub<T>(src[i], src[i - 1]);
         src[0] = slice_sub<T>(src[0], first_prev);
     } else {
-        seq_rows<RPG>([&](auto ic) {
-            constexpr int i = warp_visit_row<RPG>(decltype(ic)::value);
-            src[i] = load_slice<T>(ip + warp_row_offset<T, i>(q));
-        });
+        if constexpr (TMA) {
+            // dynamic shared memory: [8 warps x 128*T bytes | 8 mbarriers]  (u64 needs 64 KiB: opt-in attribute)
+            extern __shared__ __align__(128) unsigned char orig_tile_smem[];
+            const int wi = threadIdx.x >> 5;
+            unsigned char* tma_in = orig_tile_smem + wi * (128 * TB);
+            const unsigned bar = smem_addr(orig_tile_smem + (kThreads / 32) * (128 * TB) + wi * 8);
+            if (lane == 0) mbar_init(bar, 1);
+            __syncwarp();
+            if (lane == 0) {
+                mbar_arrive_expect_tx(bar, 128 * TB);
+                tma_bulk_load(smem_addr(tma_in), in + blk * (size_t(128) * TB), 128 * TB, bar);
+            }
+            mbar_wait_parity(bar, 0);
+            const unsigned char* sp = tma_in + j * 16;
+            seq_rows<RPG>([&](auto ic) {
+                constexpr int i = decltype(ic)::value;
+                src[i] = to_slice<T>(*reinterpret_cast<const uint4*>(sp + warp_row_offset<T, i>(q)));
+            });
+        } else {
+            seq_rows<RPG>([&](auto ic) {
+                constexpr int i = warp_visit_row<RPG>(decltype(ic)::value);
+                src[i] = load_slice<T>(ip + warp_row_offset<T, i>(q));
+            });
+        }
     }
     if constexpr (OP == POP_FOR) {
         const Slice<T> ref = slice_splat<T>(refs ? refs[blk] : ref_scalar);  // ffor.rs:33
@@ -663,7 +684,7 @@ transpose_warp_kernel(const char* __restrict__ in, char* __restrict__ out, size_
     const int lane = threadIdx.x & 31;
     const int g = lane >> 3, j = lane & 7;
     const int q = WL::rank_of_group(g);
-    extern __shared__ __align__(16) unsigned char orig_tile_smem[];
+    extern __shared__ __align__(128) unsigned char orig_tile_smem[];
     unsigned char* tile = orig_tile_smem + (threadIdx.x >> 5) * (128 * TB);
     const char* ib = in + blk * (size_t(128) * TB);
     char* ob = out + blk * (size_t(128) * TB);

@@ -127,9 +127,16 @@ static void bench_width(const Ctx& c, const std::string& op) {
     } else if (op == "undelta_pack") {
         float ms = time_ms(c, [&] { unpack_kernel<T, W, UOP_DELTA><<<grid, kThreads, 0, c.s>>>(c.in, c.out, c.n_blocks, nullptr, T(0), c.base); });
         report("undelta_pack", TB, W, c.n_blocks, 128 * (W + TB + 1), ms);
-    } else if (op == "packB" || op == "for_packB") {
+    } else if (op == "packB" || op == "packT" || op == "for_packB") {
         const unsigned gridB = unsigned((c.n_blocks * 32 + kThreads - 1) / kThreads);
-        if (op == "packB") {
+        if (op == "packT") {
+            float ms = time_ms(c, [&] { pack_warp_kernel<T, W, POP_PLAIN, true><<<gridB, kThreads, (kThreads / 32) * (128 * TB + 8), c.s>>>(c.out, c.in, c.n_blocks, nullptr, T(0), nullptr); });
+            report("packT", TB, W, c.n_blocks, 128 * (W + TB), ms);
+            const unsigned long long ct = checksum(c.in, c.n_blocks * 128 * size_t(W), c.s);
+            pack_warp_kernel<T, W, POP_PLAIN><<<gridB, kThreads, 0, c.s>>>(c.out, c.in, c.n_blocks, nullptr, T(0), nullptr);
+            const unsigned long long cb = checksum(c.in, c.n_blocks * 128 * size_t(W), c.s);
+            if (ct != cb) printf("  !! packT checksum MISMATCH at W=%d\n", W);
+        } else if (op == "packB") {
             float ms = time_ms(c, [&] { pack_warp_kernel<T, W, POP_PLAIN><<<gridB, kThreads, 0, c.s>>>(c.out, c.in, c.n_blocks, nullptr, T(0), nullptr); });
             report("packB", TB, W, c.n_blocks, 128 * (W + TB), ms);
         } else {
