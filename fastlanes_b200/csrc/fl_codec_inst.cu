@@ -39,16 +39,18 @@ static cudaError_t do_unpack(const LaunchArgs& a) {
     }
     // warp-block layout: one warp per 1024-value block (see fl_kernels.cuh)
     const unsigned grid = unsigned((a.n_blocks * 32 + kThreads - 1) / kThreads);
+    // TMA bulk load of the packed block (one cp.async.bulk per warp): measured +0.5..8% on u32 (largest at W >= 25,
+    // profiles/kbench_r01_tma_u32.txt).  u8 blocks (<= 1 KiB packed) are too small to amortise the mbarrier round
+    // trip (measured slower): direct loads.  The original-order variant also owns a dynamic shared tile; there the
+    // extra static buffer costs occupancy and the bulk copy only wins where measured: u32 at W >= 8, u64 at W % 4 != 0.
+    constexpr bool kTma = (OP != UOP_DELTA_ORIG) ? (sizeof(T) >= 2)
+                                                 : ((sizeof(T) == 4 && W >= 8) || (sizeof(T) == 8 && W % 4 != 0));
     size_t smem = 0;
     if constexpr (OP == UOP_DELTA_ORIG) {  // one block staged per warp
         smem = size_t(kThreads / 32) * 128 * Lay<T>::TB;
-        static const cudaError_t attr = cudaFuncSetAttribute(unpack_warp_kernel<T, W, OP, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, int(smem));
+        static const cudaError_t attr = cudaFuncSetAttribute(unpack_warp_kernel<T, W, OP, kTma>, cudaFuncAttributeMaxDynamicSharedMemorySize, int(smem));
         if (attr != cudaSuccess) return attr;
     }
-    // TMA bulk load of the packed block (one cp.async.bulk per warp): measured +0.5..8% on u32 (largest at W >= 25,
-    // profiles/kbench_r01_tma_u32.txt).  The original-order variant already owns a dynamic shared tile: keep it direct.
-    // u8 blocks (<= 1 KiB packed) are too small to amortise the mbarrier round trip: measured slower, keep direct.
-    constexpr bool kTma = (OP != UOP_DELTA_ORIG) && sizeof(T) >= 2;
     unpack_warp_kernel<T, W, OP, kTma><<<grid, kThreads, smem, a.stream>>>(
         static_cast<const char*>(a.in), static_cast<char*>(a.out), a.n_blocks, static_cast<const T*>(a.refs),
         T(a.ref_scalar), static_cast<const char*>(a.base));
@@ -121,8 +123,17 @@ cudaError_t launch_delta<elem_t>(bool undo, const LaunchArgs& a) {
     const char* base = static_cast<const char*>(a.base);
     char* out = static_cast<char*>(a.out);
     const unsigned grid = unsigned((a.n_blocks * 32 + kThreads - 1) / kThreads);  // warp-block layout
-    if (undo) delta_warp_kernel<elem_t, true><<<grid, kThreads, 0, a.stream>>>(in, base, out, a.n_blocks);
-    else delta_warp_kernel<elem_t, false><<<grid, kThreads, 0, a.stream>>>(in, base, out, a.n_blocks);
+    constexpr bool kTma = sizeof(elem_t) >= 2;  // TMA bulk load of the block (u8: too small to pay, see do_pack)
+    const size_t smem = kTma ? size_t(kThreads / 32) * (128 * Lay<elem_t>::TB + 8) : 0;
+    if (undo) {
+        static const cudaError_t attr = cudaFuncSetAttribute(delta_warp_kernel<elem_t, true, kTma>, cudaFuncAttributeMaxDynamicSharedMemorySize, int(smem));
+        if (attr != cudaSuccess) return attr;
+        delta_warp_kernel<elem_t, true, kTma><<<grid, kThreads, smem, a.stream>>>(in, base, out, a.n_blocks);
+    } else {
+        static const cudaError_t attr = cudaFuncSetAttribute(delta_warp_kernel<elem_t, false, kTma>, cudaFuncAttributeMaxDynamicSharedMemorySize, int(smem));
+        if (attr != cudaSuccess) return attr;
+        delta_warp_kernel<elem_t, false, kTma><<<grid, kThreads, smem, a.stream>>>(in, base, out, a.n_blocks);
+    }
     return cudaGetLastError();
 }
 

@@ -613,7 +613,7 @@ pack_warp_kernel(const char* __restrict__ in, char* __restrict__ packed, size_t 
 // ---------------------------------------------------------------------------------------------------
 // a15 Delta::delta / a16 Delta::undelta (src/delta.rs:24-45), warp-block layout.
 // ---------------------------------------------------------------------------------------------------
-template <class T, bool UNDO>
+template <class T, bool UNDO, bool TMA = false>
 __global__ void __launch_bounds__(kThreads)
 delta_warp_kernel(const char* __restrict__ in, const char* __restrict__ base, char* __restrict__ out, size_t n_blocks) {
     using R = typename Lay<T>::R;
@@ -629,11 +629,30 @@ delta_warp_kernel(const char* __restrict__ in, const char* __restrict__ base, ch
     const char* ip = in + blk * (size_t(128) * TB) + j * 16;
     char* op = out + blk * (size_t(128) * TB) + j * 16;
     Slice<T> v[RPG];
-    seq_rows<RPG>([&](auto ic) {
-        constexpr int i = warp_visit_row<RPG>(decltype(ic)::value);
-        v[i] = load_slice<T>(ip + warp_row_offset<T, i>(q));
-    });
     Slice<T> carry = load_slice<T>(base + blk * 128 + j * 16);  // delta.rs:26 / :38: prev = base[lane]
+    if constexpr (TMA) {
+        // one cp.async.bulk of the whole 128*T-byte block per warp (dynamic shared memory: 8 buffers + 8 mbarriers)
+        extern __shared__ __align__(128) unsigned char orig_tile_smem[];
+        const int wi = threadIdx.x >> 5;
+        unsigned char* buf = orig_tile_smem + wi * (128 * TB);
+        const unsigned bar = smem_addr(orig_tile_smem + (kThreads / 32) * (128 * TB) + wi * 8);
+        if (lane == 0) mbar_init(bar, 1);
+        __syncwarp();
+        if (lane == 0) {
+            mbar_arrive_expect_tx(bar, 128 * TB);
+            tma_bulk_load(smem_addr(buf), in + blk * (size_t(128) * TB), 128 * TB, bar);
+        }
+        mbar_wait_parity(bar, 0);
+        seq_rows<RPG>([&](auto ic) {
+            constexpr int i = decltype(ic)::value;
+            v[i] = to_slice<T>(*reinterpret_cast<const uint4*>(buf + j * 16 + warp_row_offset<T, i>(q)));
+        });
+    } else {
+        seq_rows<RPG>([&](auto ic) {
+            constexpr int i = warp_visit_row<RPG>(decltype(ic)::value);
+            v[i] = load_slice<T>(ip + warp_row_offset<T, i>(q));
+        });
+    }
     if constexpr (UNDO) {
 #pragma unroll
         for (int i = 1; i < RPG; ++i) v[i] = slice_add<T>(v[i], v[i - 1]);  // delta.rs:40-42 within the run
