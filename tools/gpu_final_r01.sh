@@ -9,11 +9,11 @@ timeout 900 ncu --metrics gpu__time_duration.sum --clock-control none -c 600 --c
     python bench.py --steps 2 --warmup 3 --e2e-steps 0 --no-cpu > gpurun_out/bench_under_ncu.log 2>&1
 for w in 1 16 32; do
   timeout 600 ncu --set full --clock-control none --import-source on -k regex:unpack_warp_kernel -s 3 -c 1 -f \
-      -o /tmp/prof_unpack_u32_w$w build/kbench/kb_u32 32 unpackB 20 1 $w $w > gpurun_out/ncu_w$w.log 2>&1
+      -o /tmp/prof_unpack_u32_w$w build/kbench/kb_u32 32 unpackT 20 1 $w $w > gpurun_out/ncu_w$w.log 2>&1
   ncu -i /tmp/prof_unpack_u32_w$w.ncu-rep --page raw --csv > gpurun_out/ncu_raw_unpack_u32_w$w.csv 2>/dev/null
   ncu -i /tmp/prof_unpack_u32_w$w.ncu-rep --page source --csv > gpurun_out/ncu_source_unpack_u32_w$w.csv 2>/dev/null
 done
-timeout 600 ncu --set full --clock-control none -k regex:pack_warp_kernel -s 3 -c 1 -f -o /tmp/prof_pack_u32_w16 build/kbench/kb_u32 32 packB 20 1 16 16 > gpurun_out/ncu_pack.log 2>&1
+timeout 600 ncu --set full --clock-control none -k regex:pack_warp_kernel -s 3 -c 1 -f -o /tmp/prof_pack_u32_w16 build/kbench/kb_u32 32 packT 20 1 16 16 > gpurun_out/ncu_pack.log 2>&1
 ncu -i /tmp/prof_pack_u32_w16.ncu-rep --page raw --csv > gpurun_out/ncu_raw_pack_u32_w16.csv 2>/dev/null
 timeout 600 ncu --set full --clock-control none -k regex:unpack_warp_kernel -s 3 -c 1 -f -o /tmp/prof_undelta_u32_w8 build/kbench/kb_u32 32 undelta_packB 20 1 8 8 > gpurun_out/ncu_undelta.log 2>&1
 ncu -i /tmp/prof_undelta_u32_w8.ncu-rep --page raw --csv > gpurun_out/ncu_raw_undelta_pack_u32_w8.csv 2>/dev/null
