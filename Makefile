@@ -9,8 +9,8 @@ SRC := fastlanes_b200/csrc
 OBJ := build/obj
 LIB := fastlanes_b200/lib/libfastlanes_b200.so
 TYPES := 8 16 32 64
-PARTS := 0 1 2
-HDRS := $(SRC)/fl_device.cuh $(SRC)/fl_kernels.cuh $(SRC)/fl_internal.h include/fastlanes_b200.h
+PARTS := 0 1 2 3
+HDRS := $(SRC)/fl_device.cuh $(SRC)/fl_kernels.cuh $(SRC)/fl_scan.cuh $(SRC)/fl_scan_bits.h $(SRC)/fl_internal.h include/fastlanes_b200.h
 
 CODEC_OBJS := $(foreach t,$(TYPES),$(foreach p,$(PARTS),$(OBJ)/codec_u$(t)_p$(p).o))
 OBJS := $(CODEC_OBJS) $(OBJ)/fl_misc.o $(OBJ)/fl_api.o
@@ -68,3 +68,8 @@ KBFLAGS_u32 := -DKB_ONLY_U32
 # C++ trait-mirror test binary (run on the GPU box by tests/test_gpu_cpp_traits.py)
 build/test_traits: tests/cpp/test_traits.cpp include/fastlanes_b200.hpp include/fastlanes_b200.h $(LIB)
 	g++ -std=c++17 -O1 -Iinclude -o $@ $< -Lfastlanes_b200/lib -lfastlanes_b200 -Wl,-rpath,'$$ORIGIN/../fastlanes_b200/lib'
+
+# CPU check of the scan kernels' bit arithmetic (warp emulated in lockstep; no CUDA): tests/test_scan_bits.py
+build/test_scan_bits: tests/cpp/test_scan_bits.cpp $(SRC)/fl_scan_bits.h
+	mkdir -p build
+	g++ -std=c++17 -O1 -Wall -I$(SRC) -o $@ $<

@@ -29,7 +29,7 @@ from ._lib import FastLanesError, LIB_PATH, exported_symbols  # noqa: F401
 
 FL_ORDER = (0, 4, 2, 6, 1, 5, 3, 7)  # src/lib.rs:22
 
-__all__ = ["BitPacking", "FoR", "Delta", "Transpose", "FastLanes", "FastLanesError", "FL_ORDER",
+__all__ = ["BitPacking", "FoR", "Delta", "Transpose", "Scan", "FastLanes", "FastLanesError", "FL_ORDER",
            "packed_len", "version", "device_count", "init", "host_configure", "pinned_empty", "shutdown"]
 
 
@@ -370,6 +370,75 @@ class Transpose:
     def transpose_index(idx: int) -> int:
         """`const fn transpose(idx)` (src/transpose.rs:29-36)."""
         return (idx % 16) * 64 + FL_ORDER[(idx // 16) % 8] * 8 + idx // 128
+
+
+class Scan:
+    """Fused decode + predicate.  Not a trait of the reference: its README (README.md:40-41)
+    tells callers to unpack the whole block and loop over it.  Here the decoded block stays in registers.
+
+    Value i of a block is `unfor_pack::<W>(packed, reference)[i]` (src/ffor.rs:38-50; reference 0 = plain
+    `unpack`, src/bitpacking.rs:98-107).  Bitmaps are uint8, 128 bytes per block, bit i of a block at byte i//8,
+    bit i%8 (numpy `packbits(bitorder="little")`)."""
+
+    @staticmethod
+    def filter_range(width: int, packed, reference, lo, hi, bitmap, counts=None) -> None:
+        """bitmap bit i = lo <= value[i] <= hi (unsigned, inclusive).  `reference`: scalar, or (CUDA tensors) one
+        per block.  `counts` (optional, uint32 per block) receives the number of selected values."""
+        p, b = _Arg(packed, "packed"), _Arg(bitmap, "bitmap")
+        if b.tbits != 8:
+            raise FastLanesError(_lib.FL_ERR_LEN, "bitmap must be uint8")
+        dev = p.device is not None
+        if (b.device is not None) != dev:
+            raise FastLanesError(_lib.FL_ERR_NULL, "all buffers must be host arrays or all CUDA tensors")
+        _check_width(width, p.tbits)
+        if b.n % 128:
+            raise FastLanesError(_lib.FL_ERR_LEN, "bitmap must hold 128 bytes per block")
+        n = b.n // 128
+        _expect(p, n * packed_len(p.tbits, width), "Input")
+        cptr = None
+        if counts is not None:
+            c = _Arg(counts, "counts")
+            if c.tbits != 32 or (c.device is not None) != dev:
+                raise FastLanesError(_lib.FL_ERR_LEN, "counts must be uint32 in the same memory space")
+            _expect(c, n, "Counts")
+            cptr = c.ptr
+        lo_v, hi_v = _ref_value(lo, p.tbits), _ref_value(hi, p.tbits)
+        if dev:
+            if _is_torch(reference) and reference.dim() > 0:
+                r = _Arg(reference, "reference")
+                if r.tbits != p.tbits:
+                    raise FastLanesError(_lib.FL_ERR_LEN, "all buffers must share one element type")
+                _expect(r, n, "Reference")
+                rptr, rval = r.ptr, 0
+            else:
+                rptr, rval = None, _ref_value(reference, p.tbits)
+            _lib.check(_lib.fn("fl_unpack_filter", p.tbits)(width, n, p.ptr, rptr, rval, lo_v, hi_v, b.ptr, cptr, _stream()))
+        else:
+            _lib.check(_lib.fn("fl_host_unpack_filter", p.tbits)(width, n, p.ptr, _ref_value(reference, p.tbits), lo_v,
+                                                                 hi_v, b.ptr, cptr))
+
+    @staticmethod
+    def select(width: int, packed, reference, bitmap, offsets, output) -> None:
+        """Dense compaction (CUDA tensors): output[offsets[b] + k] = k-th selected value of block b in index order;
+        `offsets` (uint64/int64 per block) = exclusive prefix sum of the per-block counts."""
+        p, b, f, o = _Arg(packed, "packed"), _Arg(bitmap, "bitmap"), _Arg(offsets, "offsets"), _Arg(output, "output")
+        if None in (p.device, b.device, f.device, o.device):
+            raise FastLanesError(_lib.FL_ERR_NULL, "select takes CUDA tensors")
+        if b.tbits != 8 or f.tbits != 64 or o.tbits != p.tbits:
+            raise FastLanesError(_lib.FL_ERR_LEN, "bitmap must be uint8, offsets 64-bit, output of the packed element type")
+        _check_width(width, p.tbits)
+        if b.n % 128:
+            raise FastLanesError(_lib.FL_ERR_LEN, "bitmap must hold 128 bytes per block")
+        n = b.n // 128
+        _expect(p, n * packed_len(p.tbits, width), "Input")
+        _expect(f, n, "Offsets")
+        if _is_torch(reference) and reference.dim() > 0:
+            r = _Arg(reference, "reference")
+            _expect(r, n, "Reference")
+            rptr, rval = r.ptr, 0
+        else:
+            rptr, rval = None, _ref_value(reference, p.tbits)
+        _lib.check(_lib.fn("fl_unpack_select", p.tbits)(width, n, p.ptr, rptr, rval, b.ptr, f.ptr, o.ptr, _stream()))
 
 
 _lib.lib()  # fail loudly at import time if the CUDA library is missing

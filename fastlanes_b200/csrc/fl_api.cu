@@ -3,6 +3,7 @@
 // Device family: argument checks + one kernel launch on the caller's stream.
 // Host family:   chunked H2D -> kernel -> D2H pipeline over internal streams (per-device context).
 // There is no CPU compute path anywhere in this library: every value is produced by a CUDA kernel.
+#include <atomic>
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
@@ -125,8 +126,8 @@ struct HostCtx {
 
 std::mutex g_ctx_mu;
 std::vector<HostCtx*> g_ctxs;
-size_t g_chunk_blocks = 16384;
-int g_n_streams = 3;
+std::atomic<size_t> g_chunk_blocks{16384};  // fl_host_configure may race with fl_host_* calls on other threads
+std::atomic<int> g_n_streams{3};
 
 fl_status get_ctx(HostCtx** out) {
     int dev = -1;
@@ -165,9 +166,11 @@ fl_status host_op(Op op, unsigned width, size_t n_blocks, const void* in, void* 
     HostCtx* ctx = nullptr;
     if (fl_status s = get_ctx(&ctx)) return s;
     std::lock_guard<std::mutex> lk(ctx->mu);
-    const size_t chunk = g_chunk_blocks ? g_chunk_blocks : 16384;
+    const size_t chunk_cfg = g_chunk_blocks.load();
+    const size_t chunk = chunk_cfg ? chunk_cfg : 16384;
     const size_t n_chunks = (n_blocks + chunk - 1) / chunk;
-    const size_t n_slots = size_t(g_n_streams > 0 ? g_n_streams : 3);
+    const int streams_cfg = g_n_streams.load();
+    const size_t n_slots = size_t(streams_cfg > 0 ? streams_cfg : 3);
     if (ctx->slots.size() < n_slots) ctx->slots.resize(n_slots);
     const size_t use_slots = n_chunks < n_slots ? n_chunks : n_slots;
     const size_t cb = n_blocks < chunk ? n_blocks : chunk;
@@ -183,13 +186,17 @@ fl_status host_op(Op op, unsigned width, size_t n_blocks, const void* in, void* 
         Slot& sl = ctx->slots[c % use_slots];
         const size_t b0 = c * chunk;
         const size_t nb = (n_blocks - b0) < chunk ? (n_blocks - b0) : chunk;
-        // stream order serialises reuse of this slot's device buffers with the previous chunk's D2H
-        if (ib) FL_CUDA(cudaMemcpyAsync(sl.d_in, static_cast<const char*>(in) + b0 * ib, nb * ib, cudaMemcpyHostToDevice, sl.stream));
-        if (op_has_base(op))
-            FL_CUDA(cudaMemcpyAsync(sl.d_base, static_cast<const char*>(base) + b0 * 128, nb * 128, cudaMemcpyHostToDevice, sl.stream));
+        // stream order serialises reuse of this slot's device buffers with the previous chunk's D2H.
+        // Errors break out to the drain loop below: no copy touching the caller's buffers may outlive the call.
+        cudaError_t e = cudaSuccess;
+        if (ib) e = cudaMemcpyAsync(sl.d_in, static_cast<const char*>(in) + b0 * ib, nb * ib, cudaMemcpyHostToDevice, sl.stream);
+        if (e == cudaSuccess && op_has_base(op))
+            e = cudaMemcpyAsync(sl.d_base, static_cast<const char*>(base) + b0 * 128, nb * 128, cudaMemcpyHostToDevice, sl.stream);
+        if (e != cudaSuccess) { result = cuda_fail(e, "cudaMemcpyAsync H2D"); break; }
         result = device_op<T>(op, width, nb, sl.d_in, sl.d_out, sl.d_base, nullptr, ref_scalar, sl.stream);
         if (result != FL_OK) break;
-        FL_CUDA(cudaMemcpyAsync(static_cast<char*>(out) + b0 * ob, sl.d_out, nb * ob, cudaMemcpyDeviceToHost, sl.stream));
+        e = cudaMemcpyAsync(static_cast<char*>(out) + b0 * ob, sl.d_out, nb * ob, cudaMemcpyDeviceToHost, sl.stream);
+        if (e != cudaSuccess) { result = cuda_fail(e, "cudaMemcpyAsync D2H"); break; }
     }
     for (size_t s = 0; s < use_slots; ++s) {
         cudaError_t e = cudaStreamSynchronize(ctx->slots[s].stream);
@@ -215,8 +222,10 @@ fl_status host_minmax(size_t n_blocks, const T* in, T* mins, T* maxs) {
     HostCtx* ctx = nullptr;
     if (fl_status s = get_ctx(&ctx)) return s;
     std::lock_guard<std::mutex> lk(ctx->mu);
-    const size_t chunk = g_chunk_blocks ? g_chunk_blocks : 16384;
-    const size_t n_slots = size_t(g_n_streams > 0 ? g_n_streams : 3);
+    const size_t chunk_cfg = g_chunk_blocks.load();
+    const size_t chunk = chunk_cfg ? chunk_cfg : 16384;
+    const int streams_cfg = g_n_streams.load();
+    const size_t n_slots = size_t(streams_cfg > 0 ? streams_cfg : 3);
     if (ctx->slots.size() < n_slots) ctx->slots.resize(n_slots);
     const size_t n_chunks = (n_blocks + chunk - 1) / chunk;
     const size_t use_slots = n_chunks < n_slots ? n_chunks : n_slots;
@@ -235,13 +244,99 @@ fl_status host_minmax(size_t n_blocks, const T* in, T* mins, T* maxs) {
         const size_t nb = (n_blocks - b0) < chunk ? (n_blocks - b0) : chunk;
         T* d_min = static_cast<T*>(sl.d_out);
         T* d_max = reinterpret_cast<T*>(static_cast<char*>(sl.d_out) + half);
-        FL_CUDA(cudaMemcpyAsync(sl.d_in, in + b0 * 1024, nb * 1024 * sizeof(T), cudaMemcpyHostToDevice, sl.stream));
+        cudaError_t e = cudaMemcpyAsync(sl.d_in, in + b0 * 1024, nb * 1024 * sizeof(T), cudaMemcpyHostToDevice, sl.stream);
+        if (e != cudaSuccess) { result = cuda_fail(e, "cudaMemcpyAsync H2D"); break; }
         result = device_minmax<T>(nb, static_cast<const T*>(sl.d_in), d_min, d_max, sl.stream);
         if (result != FL_OK) break;
-        FL_CUDA(cudaMemcpyAsync(mins + b0, d_min, nb * sizeof(T), cudaMemcpyDeviceToHost, sl.stream));
-        FL_CUDA(cudaMemcpyAsync(maxs + b0, d_max, nb * sizeof(T), cudaMemcpyDeviceToHost, sl.stream));
+        e = cudaMemcpyAsync(mins + b0, d_min, nb * sizeof(T), cudaMemcpyDeviceToHost, sl.stream);
+        if (e == cudaSuccess) e = cudaMemcpyAsync(maxs + b0, d_max, nb * sizeof(T), cudaMemcpyDeviceToHost, sl.stream);
+        if (e != cudaSuccess) { result = cuda_fail(e, "cudaMemcpyAsync D2H"); break; }
     }
     for (size_t s = 0; s < use_slots; ++s) {
+        cudaError_t e = cudaStreamSynchronize(ctx->slots[s].stream);
+        if (e != cudaSuccess && result == FL_OK) result = cuda_fail(e, "cudaStreamSynchronize");
+    }
+    return result;
+}
+
+// ---- fused scan (fl_scan.cuh) -------------------------------------------------------------------
+template <class T>
+fl_status device_filter(unsigned width, size_t n_blocks, const T* packed, const T* refs, T reference, T lo, T hi,
+                        uint8_t* bitmap, uint32_t* counts, cudaStream_t stream) {
+    if (width > sizeof(T) * 8) return fail(FL_ERR_WIDTH, "width exceeds the bit size of the element type");
+    if (n_blocks == 0) return FL_OK;
+    if (n_blocks > (size_t(1) << 40)) return fail(FL_ERR_LEN, "n_blocks too large");
+    if (!bitmap || (width && !packed)) return fail(FL_ERR_NULL, "null pointer");
+    if ((width && !aligned16(packed)) || !aligned16(bitmap)) return fail(FL_ERR_ALIGN, "device pointers must be 16-byte aligned");
+    LaunchArgs a;
+    a.in = packed; a.out = bitmap; a.counts = counts; a.refs = refs; a.ref_scalar = reference;
+    a.flo = lo; a.fhi = hi; a.n_blocks = n_blocks; a.width = width; a.stream = stream;
+    const cudaError_t e = flb::launch_filter<T>(a);
+    if (e != cudaSuccess) return cuda_fail(e, "filter launch");
+    return FL_OK;
+}
+
+template <class T>
+fl_status device_select(unsigned width, size_t n_blocks, const T* packed, const T* refs, T reference,
+                        const uint8_t* bitmap, const uint64_t* offsets, T* out, cudaStream_t stream) {
+    if (width > sizeof(T) * 8) return fail(FL_ERR_WIDTH, "width exceeds the bit size of the element type");
+    if (n_blocks == 0) return FL_OK;
+    if (n_blocks > (size_t(1) << 40)) return fail(FL_ERR_LEN, "n_blocks too large");
+    if (!bitmap || !offsets || !out || (width && !packed)) return fail(FL_ERR_NULL, "null pointer");
+    if ((width && !aligned16(packed)) || !aligned16(bitmap)) return fail(FL_ERR_ALIGN, "device pointers must be 16-byte aligned");
+    LaunchArgs a;
+    a.in = packed; a.out = out; a.bitmap = bitmap; a.offsets = offsets; a.refs = refs; a.ref_scalar = reference;
+    a.n_blocks = n_blocks; a.width = width; a.stream = stream;
+    const cudaError_t e = flb::launch_select<T>(a);
+    if (e != cudaSuccess) return cuda_fail(e, "select launch");
+    return FL_OK;
+}
+
+// host buffers: H2D of the packed chunk, filter kernel, D2H of 128 (+4) bytes per block — the decoded values never
+// cross the PCIe link
+template <class T>
+fl_status host_filter(unsigned width, size_t n_blocks, const T* packed, T reference, T lo, T hi, uint8_t* bitmap,
+                      uint32_t* counts) {
+    if (width > sizeof(T) * 8) return fail(FL_ERR_WIDTH, "width exceeds the bit size of the element type");
+    if (n_blocks == 0) return FL_OK;
+    if (!bitmap || (width && !packed)) return fail(FL_ERR_NULL, "null pointer");
+    HostCtx* ctx = nullptr;
+    if (fl_status s = get_ctx(&ctx)) return s;
+    std::lock_guard<std::mutex> lk(ctx->mu);
+    const size_t chunk_cfg = g_chunk_blocks.load();
+    const size_t chunk = chunk_cfg ? chunk_cfg : 16384;
+    const int streams_cfg = g_n_streams.load();
+    const size_t n_slots = size_t(streams_cfg > 0 ? streams_cfg : 3);
+    if (ctx->slots.size() < n_slots) ctx->slots.resize(n_slots);
+    const size_t n_chunks = (n_blocks + chunk - 1) / chunk;
+    const size_t use_slots = n_chunks < n_slots ? n_chunks : n_slots;
+    const size_t cb = n_blocks < chunk ? n_blocks : chunk;
+    const size_t ib = size_t(128) * width;
+    for (size_t s = 0; s < use_slots; ++s) {
+        Slot& sl = ctx->slots[s];
+        if (!sl.stream) FL_CUDA(cudaStreamCreateWithFlags(&sl.stream, cudaStreamNonBlocking));
+        if (ib) if (fl_status st = ensure(&sl.d_in, &sl.in_cap, cb * ib)) return st;
+        if (fl_status st = ensure(&sl.d_out, &sl.out_cap, cb * 128 + cb * sizeof(uint32_t))) return st;
+    }
+    fl_status result = FL_OK;
+    for (size_t c = 0; c < n_chunks && result == FL_OK; ++c) {
+        Slot& sl = ctx->slots[c % use_slots];
+        const size_t b0 = c * chunk;
+        const size_t nb = (n_blocks - b0) < chunk ? (n_blocks - b0) : chunk;
+        uint8_t* d_bitmap = static_cast<uint8_t*>(sl.d_out);
+        uint32_t* d_counts = reinterpret_cast<uint32_t*>(d_bitmap + cb * 128);
+        cudaError_t e = cudaSuccess;
+        if (ib) e = cudaMemcpyAsync(sl.d_in, reinterpret_cast<const char*>(packed) + b0 * ib, nb * ib, cudaMemcpyHostToDevice, sl.stream);
+        if (e != cudaSuccess) { result = cuda_fail(e, "cudaMemcpyAsync H2D"); break; }
+        result = device_filter<T>(width, nb, static_cast<const T*>(sl.d_in), nullptr, reference, lo, hi, d_bitmap,
+                                  counts ? d_counts : nullptr, sl.stream);
+        if (result != FL_OK) break;
+        e = cudaMemcpyAsync(bitmap + b0 * 128, d_bitmap, nb * 128, cudaMemcpyDeviceToHost, sl.stream);
+        if (e == cudaSuccess && counts)
+            e = cudaMemcpyAsync(counts + b0, d_counts, nb * sizeof(uint32_t), cudaMemcpyDeviceToHost, sl.stream);
+        if (e != cudaSuccess) { result = cuda_fail(e, "cudaMemcpyAsync D2H"); break; }
+    }
+    for (size_t s = 0; s < use_slots; ++s) {  // always drain: no copy may outlive the call
         cudaError_t e = cudaStreamSynchronize(ctx->slots[s].stream);
         if (e != cudaSuccess && result == FL_OK) result = cuda_fail(e, "cudaStreamSynchronize");
     }
@@ -279,15 +374,23 @@ fl_status host_gather(unsigned width, size_t n_blocks, const T* packed, const ui
     uint64_t* d_idx = reinterpret_cast<uint64_t*>(d);
     T* d_val = reinterpret_cast<T*>(d + idx_bytes);
     int* d_flag = reinterpret_cast<int*>(d + idx_bytes + val_bytes);
-    if (pbytes) FL_CUDA(cudaMemcpyAsync(sl.d_in, packed, pbytes, cudaMemcpyHostToDevice, sl.stream));
-    FL_CUDA(cudaMemcpyAsync(d_idx, gidx, idx_bytes, cudaMemcpyHostToDevice, sl.stream));
-    FL_CUDA(cudaMemsetAsync(d_flag, 0, sizeof(int), sl.stream));
-    if (fl_status st = device_gather<T>(width, n_blocks, static_cast<const T*>(sl.d_in), d_idx, n, d_val, d_flag, sl.stream))
-        return st;
     int flag = 0;
-    FL_CUDA(cudaMemcpyAsync(out, d_val, n * sizeof(T), cudaMemcpyDeviceToHost, sl.stream));
-    FL_CUDA(cudaMemcpyAsync(&flag, d_flag, sizeof(int), cudaMemcpyDeviceToHost, sl.stream));
-    FL_CUDA(cudaStreamSynchronize(sl.stream));
+    fl_status result = FL_OK;
+    cudaError_t e = cudaSuccess;
+    if (pbytes) e = cudaMemcpyAsync(sl.d_in, packed, pbytes, cudaMemcpyHostToDevice, sl.stream);
+    if (e == cudaSuccess) e = cudaMemcpyAsync(d_idx, gidx, idx_bytes, cudaMemcpyHostToDevice, sl.stream);
+    if (e == cudaSuccess) e = cudaMemsetAsync(d_flag, 0, sizeof(int), sl.stream);
+    if (e != cudaSuccess) result = cuda_fail(e, "cudaMemcpyAsync H2D");
+    if (result == FL_OK)
+        result = device_gather<T>(width, n_blocks, static_cast<const T*>(sl.d_in), d_idx, n, d_val, d_flag, sl.stream);
+    if (result == FL_OK) {
+        e = cudaMemcpyAsync(out, d_val, n * sizeof(T), cudaMemcpyDeviceToHost, sl.stream);
+        if (e == cudaSuccess) e = cudaMemcpyAsync(&flag, d_flag, sizeof(int), cudaMemcpyDeviceToHost, sl.stream);
+        if (e != cudaSuccess) result = cuda_fail(e, "cudaMemcpyAsync D2H");
+    }
+    e = cudaStreamSynchronize(sl.stream);  // always drain: `flag` and the caller's buffers must not be written later
+    if (e != cudaSuccess && result == FL_OK) result = cuda_fail(e, "cudaStreamSynchronize");
+    if (result != FL_OK) return result;
     if (flag) return fail(FL_ERR_INDEX, "index out of range");  // src/bitpacking.rs:152
     return FL_OK;
 }
@@ -322,7 +425,8 @@ fl_status fl_init(int device) {
     HostCtx* ctx = nullptr;
     if (fl_status s = get_ctx(&ctx)) return s;
     std::lock_guard<std::mutex> lk(ctx->mu);
-    const size_t n_slots = size_t(g_n_streams > 0 ? g_n_streams : 3);
+    const int streams_cfg = g_n_streams.load();
+    const size_t n_slots = size_t(streams_cfg > 0 ? streams_cfg : 3);
     if (ctx->slots.size() < n_slots) ctx->slots.resize(n_slots);
     for (Slot& sl : ctx->slots)
         if (!sl.stream) FL_CUDA(cudaStreamCreateWithFlags(&sl.stream, cudaStreamNonBlocking));
@@ -330,8 +434,8 @@ fl_status fl_init(int device) {
 }
 fl_status fl_host_configure(size_t chunk_blocks, int n_streams) {
     std::lock_guard<std::mutex> lk(g_ctx_mu);
-    g_chunk_blocks = chunk_blocks ? chunk_blocks : 16384;
-    g_n_streams = n_streams > 0 ? (n_streams > 16 ? 16 : n_streams) : 3;
+    g_chunk_blocks.store(chunk_blocks ? chunk_blocks : 16384);
+    g_n_streams.store(n_streams > 0 ? (n_streams > 16 ? 16 : n_streams) : 3);
     return FL_OK;
 }
 fl_status fl_host_alloc(void** p, size_t bytes) {
@@ -456,6 +560,18 @@ fl_status fl_shutdown(void) {
     }                                                                                                                   \
     fl_status fl_host_block_minmax_##SFX(size_t n, const T* in, T* mins, T* maxs) {                                     \
         return host_minmax<T>(n, in, mins, maxs);                                                                       \
+    }                                                                                                                   \
+    fl_status fl_unpack_filter_##SFX(unsigned width, size_t n, const T* packed, const T* refs, T reference, T lo, T hi, \
+                                     uint8_t* bitmap, uint32_t* counts, void* st) {                                    \
+        return device_filter<T>(width, n, packed, refs, reference, lo, hi, bitmap, counts, (cudaStream_t)st);           \
+    }                                                                                                                   \
+    fl_status fl_host_unpack_filter_##SFX(unsigned width, size_t n, const T* packed, T reference, T lo, T hi,           \
+                                          uint8_t* bitmap, uint32_t* counts) {                                          \
+        return host_filter<T>(width, n, packed, reference, lo, hi, bitmap, counts);                                     \
+    }                                                                                                                   \
+    fl_status fl_unpack_select_##SFX(unsigned width, size_t n, const T* packed, const T* refs, T reference,             \
+                                     const uint8_t* bitmap, const uint64_t* offsets, T* out, void* st) {                \
+        return device_select<T>(width, n, packed, refs, reference, bitmap, offsets, out, (cudaStream_t)st);             \
     }                                                                                                                   \
     fl_status fl_transpose_##SFX(size_t n, const T* in, T* out, void* st) {                                             \
         return device_op<T>(Op::Transpose, 0, n, in, out, nullptr, nullptr, 0, (cudaStream_t)st);                       \

@@ -1,9 +1,13 @@
 // fl_codec_inst.cu — instantiates the width-templated kernels for ONE element type and ONE part
-// (compile with -DFLB_TBITS=8|16|32|64 -DFLB_PART=0|1|2: 0 = unpack family, 1 = pack family, 2 = delta)
+// (compile with -DFLB_TBITS=8|16|32|64 -DFLB_PART=0|1|2|3: 0 = unpack family, 1 = pack family, 2 = delta and
+// transpose, 3 = fused scan kernels)
 // and builds the runtime-width dispatch tables: the `match width { W => ::<W>() }` of
 // src/bitpacking.rs:82-95, :115-128 in the reference.
 #include "fl_internal.h"
 #include "fl_kernels.cuh"
+#if FLB_PART == 3
+#include "fl_scan.cuh"
+#endif
 
 namespace flb {
 
@@ -115,6 +119,42 @@ cudaError_t launch_pack<elem_t>(int op, const LaunchArgs& a) {
     if (op == kPackPlain) return plain[a.width](a);
     if (op == kPackFor) return ffor[a.width](a);
     return cudaErrorNotSupported;
+}
+#elif FLB_PART == 3
+// fused decode + predicate kernels (fl_scan.cuh); same load-path choice as the plain unpack (TMA for u16/u32/u64)
+template <class T, int W>
+static cudaError_t do_filter(const LaunchArgs& a) {
+    const unsigned grid = unsigned((a.n_blocks * 32 + kThreads - 1) / kThreads);
+    filter_warp_kernel<T, W, (sizeof(T) >= 2)><<<grid, kThreads, 0, a.stream>>>(
+        static_cast<const char*>(a.in), static_cast<unsigned char*>(a.out), a.counts, a.n_blocks,
+        static_cast<const T*>(a.refs), T(a.ref_scalar), T(a.flo), T(a.fhi));
+    return cudaGetLastError();
+}
+template <class T, int W>
+static cudaError_t do_select(const LaunchArgs& a) {
+    const unsigned grid = unsigned((a.n_blocks * 32 + kThreads - 1) / kThreads);
+    select_warp_kernel<T, W, (sizeof(T) >= 2)><<<grid, kThreads, 0, a.stream>>>(
+        static_cast<const char*>(a.in), static_cast<const unsigned char*>(a.bitmap), a.offsets, static_cast<T*>(a.out),
+        a.n_blocks, static_cast<const T*>(a.refs), T(a.ref_scalar));
+    return cudaGetLastError();
+}
+template <class T, int... W>
+static constexpr std::array<launch_fn, sizeof...(W)> filter_table(std::integer_sequence<int, W...>) {
+    return {{&do_filter<T, W>...}};
+}
+template <class T, int... W>
+static constexpr std::array<launch_fn, sizeof...(W)> select_table(std::integer_sequence<int, W...>) {
+    return {{&do_select<T, W>...}};
+}
+template <>
+cudaError_t launch_filter<elem_t>(const LaunchArgs& a) {
+    static constexpr auto tab = filter_table<elem_t>(std::make_integer_sequence<int, Lay<elem_t>::TB + 1>{});
+    return tab[a.width](a);
+}
+template <>
+cudaError_t launch_select<elem_t>(const LaunchArgs& a) {
+    static constexpr auto tab = select_table<elem_t>(std::make_integer_sequence<int, Lay<elem_t>::TB + 1>{});
+    return tab[a.width](a);
 }
 #else
 template <>

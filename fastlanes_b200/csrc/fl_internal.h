@@ -15,6 +15,11 @@ struct LaunchArgs {
     size_t n_blocks = 0;
     unsigned width = 0;
     cudaStream_t stream = nullptr;
+    // fused scan kernels (fl_scan.cuh)
+    const void* bitmap = nullptr;       // select: n_blocks x 128 bytes (filter writes its bitmap to `out`)
+    const uint64_t* offsets = nullptr;  // select: exclusive prefix of the per-block selected counts
+    uint32_t* counts = nullptr;         // filter: optional per-block popcount
+    uint64_t flo = 0, fhi = 0;          // filter: inclusive value range
 };
 
 // op codes of launch_unpack / launch_pack (match UnpackOp / PackOp in fl_kernels.cuh)
@@ -26,6 +31,8 @@ template <class T> cudaError_t launch_unpack(int op, const LaunchArgs& a);
 template <class T> cudaError_t launch_pack(int op, const LaunchArgs& a);
 template <class T> cudaError_t launch_delta(bool undo, const LaunchArgs& a);
 template <class T> cudaError_t launch_transpose_warp(bool undo, const LaunchArgs& a);
+template <class T> cudaError_t launch_filter(const LaunchArgs& a);  // in = packed, out = bitmap
+template <class T> cudaError_t launch_select(const LaunchArgs& a);  // in = packed, out = dense values
 
 // Defined for all types in fl_misc.cu.
 template <class T> cudaError_t launch_transpose(bool undo, const LaunchArgs& a);

@@ -312,35 +312,27 @@ __device__ __forceinline__ typename Lay<T>::R lane_funnel_left_rt(typename Lay<T
     }
 }
 
+// warp_decode_tile: the decode core shared by the unpack family and the fused scan kernels.  Fills the row-major
+// register tile v[i] = 16-byte slice j of row q*RPG + i of block `blk_packed` (this thread: group rank q, slice j).
 // TMA = true: the block's 128*W packed bytes arrive with ONE cp.async.bulk (TMA 1-D bulk copy) per warp into a
 // warp-private shared buffer, completion on a per-warp mbarrier; the word-rows are then read with LDS.128.  Every
 // packed byte crosses L2 exactly once (the direct path re-reads the word-rows that two groups share when W % 4 != 0).
-template <class T, int W, int OP, bool TMA = false>
-__global__ void __launch_bounds__(kThreads)
-unpack_warp_kernel(const char* __restrict__ packed, char* __restrict__ out, size_t n_blocks,
-                   const T* __restrict__ refs, T ref_scalar, const char* __restrict__ base) {
+// Callers issue their independent global loads (delta bases) BEFORE this call: the mbarrier wait is a compiler
+// memory barrier, anything after it would be serialised behind the TMA round trip.
+// RESERVE: static shared memory (bytes) the calling kernel declares for itself (counts against the 48 KiB limit).
+template <class T, int W, bool TMA, int RESERVE = 0>
+__device__ __forceinline__ void warp_decode_tile(const char* __restrict__ blk_packed, int lane, int q, int j,
+                                                 Slice<T> (&v)[WarpLay<T>::RPG]) {
     using R = typename Lay<T>::R;
-    using WL = WarpLay<T>;
     constexpr int TB = Lay<T>::TB;
-    constexpr int RPG = WL::RPG;
+    constexpr int RPG = WarpLay<T>::RPG;
     constexpr int NR = Lay<T>::NR;
-    const size_t blk = (size_t(blockIdx.x) * kThreads + threadIdx.x) >> 5;
-    if (blk >= n_blocks) return;  // warp-uniform
-    const int lane = threadIdx.x & 31;
-    const int g = lane >> 3, j = lane & 7;
-    const int q = WL::rank_of_group(g);
-
-    const char* pk = packed + blk * (size_t(128) * W) + j * 16;
-    char* o = out + blk * (size_t(128) * TB) + j * 16;
+    const char* pk = blk_packed + j * 16;
 
     // word-row k of this block, this thread's 16-byte slice
-    constexpr bool USE_TMA = TMA && W > 0 && (kThreads / 32) * 128 * W + 128 <= 48 * 1024;  // static shared-memory limit (u64: W <= 47)
+    constexpr bool USE_TMA = TMA && W > 0 && (kThreads / 32) * 128 * W + 128 + RESERVE <= 48 * 1024;  // static shared-memory limit (u64: W <= 47)
     __shared__ __align__(128) unsigned char tma_buf[USE_TMA ? kThreads / 32 : 1][USE_TMA ? 128 * W : 16];
     __shared__ __align__(8) unsigned long long tma_bar[USE_TMA ? kThreads / 32 : 1];
-    // issue the independent global loads (delta bases) BEFORE waiting on the bulk copy: the mbarrier wait is a
-    // compiler memory barrier, anything after it would be serialised behind the TMA round trip
-    Slice<T> carry = slice_zero<T>();
-    if constexpr (OP == UOP_DELTA || OP == UOP_DELTA_ORIG) carry = load_slice<T>(base + blk * 128 + j * 16);
     const unsigned char* sp = nullptr;
     if constexpr (USE_TMA) {
         const int wi = threadIdx.x >> 5;
@@ -349,7 +341,7 @@ unpack_warp_kernel(const char* __restrict__ packed, char* __restrict__ out, size
         __syncwarp();
         if (lane == 0) {
             mbar_arrive_expect_tx(bar, 128 * W);
-            tma_bulk_load(smem_addr(&tma_buf[wi][0]), packed + blk * (size_t(128) * W), 128 * W, bar);
+            tma_bulk_load(smem_addr(&tma_buf[wi][0]), blk_packed, 128 * W, bar);
         }
         mbar_wait_parity(bar, 0);
         sp = &tma_buf[wi][0] + j * 16;
@@ -359,7 +351,6 @@ unpack_warp_kernel(const char* __restrict__ packed, char* __restrict__ out, size
         else return load_slice<T>(pk + k * 128);
     };
 
-    Slice<T> v[RPG];
     if constexpr (W == 0) {
 #pragma unroll
         for (int i = 0; i < RPG; ++i) v[i] = slice_zero<T>();
@@ -402,6 +393,29 @@ unpack_warp_kernel(const char* __restrict__ packed, char* __restrict__ out, size
             v[i] = extract_row<T, W, i>(a[idx], a[nxt]);
         });
     }
+}
+
+template <class T, int W, int OP, bool TMA = false>
+__global__ void __launch_bounds__(kThreads)
+unpack_warp_kernel(const char* __restrict__ packed, char* __restrict__ out, size_t n_blocks,
+                   const T* __restrict__ refs, T ref_scalar, const char* __restrict__ base) {
+    using R = typename Lay<T>::R;
+    using WL = WarpLay<T>;
+    constexpr int TB = Lay<T>::TB;
+    constexpr int RPG = WL::RPG;
+    constexpr int NR = Lay<T>::NR;
+    const size_t blk = (size_t(blockIdx.x) * kThreads + threadIdx.x) >> 5;
+    if (blk >= n_blocks) return;  // warp-uniform
+    const int lane = threadIdx.x & 31;
+    const int g = lane >> 3, j = lane & 7;
+    const int q = WL::rank_of_group(g);
+    char* o = out + blk * (size_t(128) * TB) + j * 16;
+
+    // prev = base[lane] (delta.rs:50): issued before the decode's TMA wait
+    Slice<T> carry = slice_zero<T>();
+    if constexpr (OP == UOP_DELTA || OP == UOP_DELTA_ORIG) carry = load_slice<T>(base + blk * 128 + j * 16);
+    Slice<T> v[RPG];
+    warp_decode_tile<T, W, TMA>(packed + blk * (size_t(128) * W), lane, q, j, v);
 
     if constexpr (OP == UOP_FOR) {
         const Slice<T> ref = slice_splat<T>(refs ? refs[blk] : ref_scalar);  // ffor.rs:47

@@ -1,0 +1,145 @@
+// fl_scan.cuh — fused decode + predicate kernels ("unpack then filter / take").
+//
+// The reference has no such operator: its README tells callers that more than ~10 random accesses should unpack
+// the whole block (README.md:40-41), i.e. a scan is `unpack` / `unfor_pack` (src/bitpacking.rs:98-107,
+// src/ffor.rs:38-50) followed by the caller's own loop over the 1024 values.  On the GPU the materialised block
+// is the expensive part (128*T bytes written per 128*W read), so these kernels keep the decoded tile in registers:
+//
+//   filter_warp_kernel : bit i of the block's 1024-bit bitmap = lo <= (unpack(packed)[i] + reference) <= hi
+//                        reads 128*W, writes 128 (+4 with counts) bytes per block
+//   select_warp_kernel : out[offsets[b] + rank_b(i)] = unpack(packed)[i] + reference for every set bit i of block b,
+//                        in index order (stream compaction given the exclusive prefix of the block counts)
+//                        reads 128*W + 128 + 8, writes sizeof(T) * selected bytes per block
+//
+// Both reuse warp_decode_tile (the decode core of unpack_warp_kernel), one warp = one block.  Bit i of a block
+// refers to the ORIGINAL value index i of the unpacked vector, i.e. exactly the element `output[i]` that
+// BitPacking::unpack would have produced (index(row,lane), src/macros.rs:20-24); the bitmap is little-endian
+// (byte i/8, bit i%8), the layout of an Arrow validity/selection buffer.
+#pragma once
+#include "fl_kernels.cuh"
+#include "fl_scan_bits.h"
+
+namespace flb {
+
+// predicate bits of one 16-byte slice: bit k = lane k passes  (v - c) <= span  (lane-wise, wrapping, unsigned)
+template <class T>
+__device__ __forceinline__ uint32_t slice_range_bits(const Slice<T>& v, typename Lay<T>::R c, typename Lay<T>::R span) {
+    uint32_t b = 0;
+    if constexpr (sizeof(T) >= 4) {
+#pragma unroll
+        for (int r = 0; r < Lay<T>::NR; ++r) b |= uint32_t((v.r[r] - c) <= span) << r;
+    } else if constexpr (sizeof(T) == 2) {
+#pragma unroll
+        for (int r = 0; r < 4; ++r) b |= mask_halves_to_bits(__vcmpleu2(__vsub2(v.r[r], c), span)) << (2 * r);
+    } else {
+#pragma unroll
+        for (int r = 0; r < 4; ++r) b |= mask_bytes_to_bits(__vcmpleu4(__vsub4(v.r[r], c), span)) << (4 * r);
+    }
+    return b;
+}
+
+template <class T, int W, bool TMA>
+__global__ void __launch_bounds__(kThreads)
+filter_warp_kernel(const char* __restrict__ packed, unsigned char* __restrict__ bitmap, uint32_t* __restrict__ counts,
+                   size_t n_blocks, const T* __restrict__ refs, T ref_scalar, T lo, T hi) {
+    using R = typename Lay<T>::R;
+    using WL = WarpLay<T>;
+    constexpr int TB = Lay<T>::TB;
+    constexpr int RPG = WL::RPG;
+    constexpr int BPT = 128 / TB;  // predicate bits per thread per row
+    const size_t blk = (size_t(blockIdx.x) * kThreads + threadIdx.x) >> 5;
+    if (blk >= n_blocks) return;  // warp-uniform
+    const int lane = threadIdx.x & 31;
+    const int g = lane >> 3, j = lane & 7;
+    const int q = WL::rank_of_group(g);
+    const T ref = refs ? refs[blk] : ref_scalar;  // issued before the decode's TMA wait
+    Slice<T> v[RPG];
+    warp_decode_tile<T, W, TMA, (kThreads / 32) * 128>(packed + blk * (size_t(128) * W), lane, q, j, v);
+
+    // value = v + ref (ffor.rs:47, wrapping).  lo <= value <= hi  <=>  (v - (lo - ref)) mod 2^T <= hi - lo
+    const Slice<T> cs = slice_splat<T>(T(lo - ref)), ss = slice_splat<T>(T(hi - lo));
+    const R c = cs.r[0], span = ss.r[0];
+    uint32_t x = 0;
+#pragma unroll
+    for (int i = 0; i < RPG; ++i) x |= slice_range_bits<T>(v[i], c, span) << (i * BPT);
+    if (hi < lo) x = 0;  // empty range
+
+    __shared__ __align__(16) unsigned char scan_tile[kThreads / 32][128];
+    unsigned char* tile = scan_tile[threadIdx.x >> 5];
+    if constexpr (sizeof(T) == 4) {
+        x = merge_pair_bpt4(x, __shfl_xor_sync(0xffffffffu, x, 1), j);
+    } else if constexpr (sizeof(T) == 8) {
+        x = merge_pair_bpt2(x, __shfl_xor_sync(0xffffffffu, x, 1), j);
+        x = merge_quad_bpt2(x, __shfl_xor_sync(0xffffffffu, x, 2), j);
+    }
+    scan_store<TB>(tile, q, j, x);
+    __syncwarp();
+    const uint32_t word = reinterpret_cast<const uint32_t*>(tile)[lane];
+    reinterpret_cast<uint32_t*>(bitmap + blk * 128)[lane] = word;  // one 128-byte line per warp
+    if (counts != nullptr) {
+        const uint32_t n = __reduce_add_sync(0xffffffffu, uint32_t(__popc(word)));
+        if (lane == 0) counts[blk] = n;
+    }
+}
+
+// lane k (0 .. 16/sizeof(T) - 1) of a 16-byte slice
+template <class T>
+__device__ __forceinline__ T slice_lane(const Slice<T>& s, int k) {
+    if constexpr (sizeof(T) >= 4) return T(s.r[k]);
+    else if constexpr (sizeof(T) == 2) return T(s.r[k >> 1] >> (16 * (k & 1)));
+    else return T(s.r[k >> 2] >> (8 * (k & 3)));
+}
+
+template <class T, int W, bool TMA>
+__global__ void __launch_bounds__(kThreads)
+select_warp_kernel(const char* __restrict__ packed, const unsigned char* __restrict__ bitmap,
+                   const uint64_t* __restrict__ offsets, T* __restrict__ out, size_t n_blocks,
+                   const T* __restrict__ refs, T ref_scalar) {
+    using WL = WarpLay<T>;
+    constexpr int TB = Lay<T>::TB;
+    constexpr int RPG = WL::RPG;
+    constexpr int BPT = 128 / TB;
+    const size_t blk = (size_t(blockIdx.x) * kThreads + threadIdx.x) >> 5;
+    if (blk >= n_blocks) return;  // warp-uniform
+    const int lane = threadIdx.x & 31;
+    const int g = lane >> 3, j = lane & 7;
+    const int q = WL::rank_of_group(g);
+    // independent loads first (before the decode's TMA wait)
+    const uint32_t mword = reinterpret_cast<const uint32_t*>(bitmap + blk * 128)[lane];
+    const uint64_t obase = offsets[blk];
+    const T ref = refs ? refs[blk] : ref_scalar;
+    // exclusive prefix of the per-word popcounts: rank of the first bit of word `lane` among the block's set bits
+    const uint32_t cnt = uint32_t(__popc(mword));
+    uint32_t incl = cnt;
+#pragma unroll
+    for (int d = 1; d < 32; d <<= 1) {
+        const uint32_t t = __shfl_up_sync(0xffffffffu, incl, d);
+        if (lane >= d) incl += t;
+    }
+    if (__shfl_sync(0xffffffffu, incl, 31) == 0) return;  // nothing selected in this block: skip the decode
+    __shared__ uint2 sel_tile[kThreads / 32][32];  // (bitmap word, exclusive prefix)
+    uint2* tile = sel_tile[threadIdx.x >> 5];
+    tile[lane] = make_uint2(mword, incl - cnt);
+    __syncwarp();
+
+    Slice<T> v[RPG];
+    warp_decode_tile<T, W, TMA, (kThreads / 32) * 256>(packed + blk * (size_t(128) * W), lane, q, j, v);
+    const Slice<T> rs = slice_splat<T>(ref);
+    T* o = out + obase;
+#pragma unroll
+    for (int i = 0; i < RPG; ++i) {
+        const int bit0 = row_bitmap_byte(q * RPG + i) * 8 + j * BPT;  // original index of this thread's first lane in row i
+        const uint2 e = tile[bit0 >> 5];
+        const int sh = bit0 & 31;
+        uint32_t bits = (e.x >> sh) & ((BPT == 32) ? 0xffffffffu : ((1u << BPT) - 1u));
+        if (bits == 0) continue;
+        uint32_t pos = e.y + uint32_t(__popc(e.x & ((1u << sh) - 1u)));
+        const Slice<T> val = slice_add<T>(v[i], rs);  // ffor.rs:47
+#pragma unroll
+        for (int k = 0; k < BPT; ++k) {
+            if ((bits >> k) & 1u) o[pos++] = slice_lane<T>(val, k);
+        }
+    }
+}
+
+}  // namespace flb

@@ -1,0 +1,92 @@
+// fl_scan_bits.h — pure bit arithmetic of the fused scan kernels (fl_scan.cuh), kept free of CUDA intrinsics so
+// that tests/cpp/test_scan_bits.cpp can run the exact same functions on the CPU against a brute-force bitmap.
+//
+// Setting.  In the warp-block layout (fl_kernels.cuh) thread (q, j) of a warp holds, for each of its RPG = T/4
+// rows i (global row r = q*RPG + i), the 16-byte slice j of the row = BPT = 128/T consecutive lanes.  A predicate
+// over those values gives the thread exactly RPG*BPT = 32 bits X, row i at bits [i*BPT, (i+1)*BPT).  The block's
+// selection bitmap is indexed by the ORIGINAL value index (bit index(r, lane) = FL_ORDER[r/8]*16 + (r%8)*128 + lane,
+// src/macros.rs:20-24), so row r owns the aligned run of L = 1024/T bits starting at row_bit_offset(r), and thread j
+// owns BPT of them.  For BPT >= 8 (u8, u16) a thread's bits are whole bytes; for BPT = 4 / 2 (u32, u64) two / four
+// neighbouring threads exchange X through warp shuffles and each assembles 4 whole bytes (4 rows x 8 lanes).
+#pragma once
+#include <cstdint>
+
+#ifdef __CUDACC__
+#define FLB_HD __host__ __device__ __forceinline__
+#else
+#define FLB_HD inline
+#endif
+
+namespace flb {
+
+// 4 nibbles (16 bits) -> the low nibbles of 4 bytes
+FLB_HD uint32_t spread4(uint32_t a) {
+    a = (a | (a << 8)) & 0x00FF00FFu;
+    a = (a | (a << 4)) & 0x0F0F0F0Fu;
+    return a;
+}
+// 8 two-bit fields (16 bits) -> the low two bits of 8 nibbles
+FLB_HD uint32_t spread2(uint32_t a) {
+    a = spread4(a);
+    a = (a | (a << 2)) & 0x33333333u;
+    return a;
+}
+
+// FL_ORDER[i] (src/lib.rs:22) without a table: nibble i of 0x73516240
+FLB_HD int scan_fl_order(int i) { return int((0x73516240u >> (4 * i)) & 7u); }
+
+// byte offset inside the 128-byte block bitmap of the L-bit run owned by row r: index(r, 0) / 8
+FLB_HD int row_bitmap_byte(int r) { return scan_fl_order(r >> 3) * 2 + (r & 7) * 16; }
+
+// u32 (BPT = 4, RPG = 8): `mine` = this thread's X, `other` = X of thread j^1.  Returns 4 bytes: byte ii = lanes
+// 8*(j>>1) .. +7 of local row 4*(j&1) + ii.
+FLB_HD uint32_t merge_pair_bpt4(uint32_t mine, uint32_t other, int j) {
+    const int h = j & 1;
+    const uint32_t lo = h ? other : mine, hi = h ? mine : other;
+    return spread4((lo >> (16 * h)) & 0xFFFFu) | (spread4((hi >> (16 * h)) & 0xFFFFu) << 4);
+}
+// u64 (BPT = 2, RPG = 16), step 1: returns 8 nibbles: nibble ii = lanes 4*(j>>1) .. +3 of local row 8*(j&1) + ii.
+FLB_HD uint32_t merge_pair_bpt2(uint32_t mine, uint32_t other, int j) {
+    const int h = j & 1;
+    const uint32_t lo = h ? other : mine, hi = h ? mine : other;
+    return spread2((lo >> (16 * h)) & 0xFFFFu) | (spread2((hi >> (16 * h)) & 0xFFFFu) << 2);
+}
+// u64 step 2: `mine` / `other` = step-1 results of threads j and j^2.  Returns 4 bytes: byte ii = lanes
+// 8*(j>>2) .. +7 of local row 8*(j&1) + 4*((j>>1)&1) + ii.
+FLB_HD uint32_t merge_quad_bpt2(uint32_t mine, uint32_t other, int j) {
+    const int h = (j >> 1) & 1;
+    const uint32_t lo = h ? other : mine, hi = h ? mine : other;
+    return spread4((lo >> (16 * h)) & 0xFFFFu) | (spread4((hi >> (16 * h)) & 0xFFFFu) << 4);
+}
+
+// SWAR comparison masks -> packed predicate bits
+// u8: m holds 0xFF / 0x00 per byte -> 4 bits (bit k = byte k)
+FLB_HD uint32_t mask_bytes_to_bits(uint32_t m) { return ((m & 0x08040201u) * 0x01010101u) >> 24; }
+// u16: m holds 0xFFFF / 0x0000 per half -> 2 bits
+FLB_HD uint32_t mask_halves_to_bits(uint32_t m) { return ((m & 0x00020001u) * 0x00010001u) >> 16; }
+
+// Stores a thread's assembled word into the warp's 128-byte bitmap tile.  `z` is, per element size:
+//   u8  : X itself                (2 rows x 16 lanes: two 16-bit stores)
+//   u16 : X itself                (4 rows x  8 lanes: four byte stores)
+//   u32 : merge_pair_bpt4 result  (4 rows x  8 lanes of the thread PAIR)
+//   u64 : merge_quad_bpt2 result  (4 rows x  8 lanes of the thread QUAD)
+// q = rank of the thread's group in row order (rows q*RPG .. q*RPG + RPG-1), j = slice index 0..7.
+template <int TBITS>
+FLB_HD void scan_store(unsigned char* tile, int q, int j, uint32_t z) {
+    if (TBITS == 8) {
+        for (int i = 0; i < 2; ++i) {
+            unsigned char* p = tile + row_bitmap_byte(q * 2 + i) + 2 * j;
+            p[0] = (unsigned char)(z >> (16 * i));
+            p[1] = (unsigned char)(z >> (16 * i + 8));
+        }
+    } else if (TBITS == 16) {
+        for (int i = 0; i < 4; ++i) tile[row_bitmap_byte(q * 4 + i) + j] = (unsigned char)(z >> (8 * i));
+    } else if (TBITS == 32) {
+        for (int ii = 0; ii < 4; ++ii) tile[row_bitmap_byte(q * 8 + 4 * (j & 1) + ii) + (j >> 1)] = (unsigned char)(z >> (8 * ii));
+    } else {
+        for (int ii = 0; ii < 4; ++ii)
+            tile[row_bitmap_byte(q * 16 + 8 * (j & 1) + 4 * ((j >> 1) & 1) + ii) + (j >> 2)] = (unsigned char)(z >> (8 * ii));
+    }
+}
+
+}  // namespace flb

@@ -125,6 +125,21 @@ FL_API fl_status fl_shutdown(void);
      * n_blocks elements each. */                                                                                   \
     FL_API fl_status fl_block_minmax_##SFX(size_t n_blocks, const T* in, T* mins, T* maxs, void* stream);                  \
     FL_API fl_status fl_host_block_minmax_##SFX(size_t n_blocks, const T* in, T* mins, T* maxs);                           \
+    /* FUSED scan (not a trait method of the reference — README.md:40-41 tells callers to     \
+     * unpack the whole block and loop over it): decode in registers, apply a range predicate, never materialise the \
+     * block.  value[i] = unfor_pack(packed, reference)[i] (src/ffor.rs:38-50; reference 0 = plain unpack,           \
+     * src/bitpacking.rs:98-107); `refs` (nullable) = one reference per block, else the scalar `reference`.          \
+     * filter: bit i of block b (bitmap byte b*128 + i/8, bit i%8; i = index in the unpacked block) =                \
+     *         lo <= value[i] <= hi (unsigned, inclusive; hi < lo selects nothing).  bitmap: n_blocks*128 bytes;     \
+     *         counts (nullable): n_blocks selected-value counts.                                                    \
+     * select: out[offsets[b] + k] = the k-th selected value of block b in index order (offsets = exclusive prefix   \
+     *         sum of the counts: dense stream compaction).  Device pointers only. */                                \
+    FL_API fl_status fl_unpack_filter_##SFX(unsigned width, size_t n_blocks, const T* packed, const T* refs, T reference,  \
+                                     T lo, T hi, uint8_t* bitmap, uint32_t* counts, void* stream);                  \
+    FL_API fl_status fl_host_unpack_filter_##SFX(unsigned width, size_t n_blocks, const T* packed, T reference, T lo,      \
+                                          T hi, uint8_t* bitmap, uint32_t* counts);                                 \
+    FL_API fl_status fl_unpack_select_##SFX(unsigned width, size_t n_blocks, const T* packed, const T* refs, T reference,  \
+                                     const uint8_t* bitmap, const uint64_t* offsets, T* out, void* stream);         \
     /* Transpose::transpose / untranspose — src/transpose.rs:5-6 (impl :11-22) */                                   \
     FL_API fl_status fl_transpose_##SFX(size_t n_blocks, const T* in, T* out, void* stream);                               \
     FL_API fl_status fl_untranspose_##SFX(size_t n_blocks, const T* in, T* out, void* stream);                             \

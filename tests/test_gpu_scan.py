@@ -1,0 +1,158 @@
+"""-m gpu: the fused scan kernels (fl_unpack_filter / fl_unpack_select) against the
+composition they replace: oracle `unfor_pack` (src/ffor.rs:38-50) / `unpack` (src/bitpacking.rs:98-107) followed by
+the caller-side loop over the 1024 values (README.md:40-41) — here numpy compare / packbits / boolean take.
+Bit-exact, every element type and every width, through the C ABI."""
+import numpy as np
+import pytest
+
+from gpu_util import DT, dev_empty, mask, rand_bytes, to_dev, to_host
+
+pytestmark = pytest.mark.gpu
+
+N_BLOCKS = 37  # ragged against the 8-blocks-per-CTA tiling
+
+
+@pytest.fixture(scope="module")
+def fl():
+    import torch
+
+    assert torch.cuda.is_available(), "gpu tests need a CUDA device"
+    import fastlanes_b200
+
+    return fastlanes_b200
+
+
+def expected_bitmap(values: np.ndarray, lo: int, hi: int) -> np.ndarray:
+    sel = (values >= values.dtype.type(lo)) & (values <= values.dtype.type(hi)) if lo <= hi else np.zeros(values.shape, bool)
+    return np.packbits(sel, bitorder="little"), sel
+
+
+def ranges_for(rng, tb: int, w: int):
+    """A few (reference, lo, hi) triples: mid-range band, equality, empty (hi < lo), everything, wrap-around ref."""
+    full = mask(tb)
+    m = mask(w) if w else 0
+    mid_lo, mid_hi = m // 4, m // 2 + 1
+    r = int(rng.integers(0, 1 << min(tb, 62)))
+    return [
+        (0, mid_lo, mid_hi),
+        (0, m // 3, m // 3),
+        (0, 5, 4),
+        (0, 0, full),
+        (r, (r + mid_lo) & full, (r + mid_hi) & full),  # may wrap to hi < lo: then nothing is selected
+        (full, 0, mid_hi),  # reference = -1: values wrap
+    ]
+
+
+@pytest.mark.parametrize("tb", [8, 16, 32, 64])
+def test_filter_every_width_device(fl, oracle, tb):
+    import torch
+
+    rng = np.random.default_rng(900 + tb)
+    for w in range(tb + 1):
+        packed = rand_bytes(rng, N_BLOCKS * 128 * w, tb)
+        d_packed = to_dev(packed)
+        for ref, lo, hi in ranges_for(rng, tb, w):
+            values = oracle.unfor_pack(packed, ref, w, n_blocks=N_BLOCKS)
+            want, sel = expected_bitmap(values, lo, hi)
+            bitmap = torch.full((N_BLOCKS * 128,), 0xA5, dtype=torch.uint8, device="cuda")
+            counts = torch.full((N_BLOCKS,), -1, dtype=torch.int32, device="cuda")
+            fl.Scan.filter_range(w, d_packed, ref, lo, hi, bitmap, counts)
+            assert np.array_equal(bitmap.cpu().numpy(), want), (tb, w, ref, lo, hi)
+            assert np.array_equal(counts.cpu().numpy().view(np.uint32), sel.reshape(N_BLOCKS, 1024).sum(1).astype(np.uint32)), (tb, w, "counts")
+
+
+@pytest.mark.parametrize("tb", [8, 16, 32, 64])
+def test_filter_per_block_references(fl, oracle, tb):
+    import torch
+
+    rng = np.random.default_rng(950 + tb)
+    for w in (0, 1, tb // 2 - 1, tb // 2, tb - 1, tb):
+        packed = rand_bytes(rng, N_BLOCKS * 128 * w, tb)
+        refs = rand_bytes(rng, N_BLOCKS * (tb // 8), tb)
+        values = oracle.unfor_pack(packed, refs, w, n_blocks=N_BLOCKS)
+        lo, hi = int(mask(tb) // 3), int(mask(tb) // 3 * 2)
+        want, _ = expected_bitmap(values, lo, hi)
+        bitmap = torch.zeros(N_BLOCKS * 128, dtype=torch.uint8, device="cuda")
+        fl.Scan.filter_range(w, to_dev(packed), to_dev(refs), lo, hi, bitmap)
+        assert np.array_equal(bitmap.cpu().numpy(), want), (tb, w)
+
+
+@pytest.mark.parametrize("tb", [8, 16, 32, 64])
+def test_select_every_width_device(fl, oracle, tb):
+    import torch
+
+    rng = np.random.default_rng(1000 + tb)
+    for w in range(tb + 1):
+        packed = rand_bytes(rng, N_BLOCKS * 128 * w, tb)
+        ref = int(rng.integers(0, 1 << min(tb, 62)))
+        values = oracle.unfor_pack(packed, ref, w, n_blocks=N_BLOCKS)
+        # selection bitmaps independent of the values: random density per block incl. empty and full blocks
+        sel = rng.random(N_BLOCKS * 1024) < np.repeat(rng.choice([0.0, 0.02, 0.5, 0.97, 1.0], N_BLOCKS), 1024)
+        bitmap = np.packbits(sel, bitorder="little")
+        counts = sel.reshape(N_BLOCKS, 1024).sum(1).astype(np.int64)
+        offsets = np.concatenate([[0], np.cumsum(counts)[:-1]]).astype(np.int64)
+        total = int(counts.sum())
+        out = dev_empty(total + 16, tb)
+        out.fill_(0x3C if tb == 8 else 0x3C3C)
+        fl.Scan.select(w, to_dev(packed), ref, torch.from_numpy(bitmap).cuda(), torch.from_numpy(offsets).cuda(), out)
+        got = to_host(out, tb)
+        assert np.array_equal(got[:total], values[sel]), (tb, w)
+        assert np.all(got[total:] == DT[tb](0x3C if tb == 8 else 0x3C3C)), (tb, w, "wrote past the selected count")
+
+
+def test_filter_then_select_pipeline_u32(fl, oracle):
+    """filter -> exclusive scan of the counts (torch.cumsum, plumbing) -> select == values[lo <= values <= hi]."""
+    import torch
+
+    rng = np.random.default_rng(77)
+    n, w, ref = 4099, 13, 1000
+    packed = rand_bytes(rng, n * 128 * w, 32)
+    d_packed = to_dev(packed)
+    lo, hi = 2000, 4000
+    bitmap = torch.empty(n * 128, dtype=torch.uint8, device="cuda")
+    counts = torch.empty(n, dtype=torch.int32, device="cuda")
+    fl.Scan.filter_range(w, d_packed, ref, lo, hi, bitmap, counts)
+    c64 = counts.to(torch.int64)
+    offsets = torch.cumsum(c64, 0) - c64
+    total = int(c64.sum().item())
+    out = dev_empty(max(total, 1), 32)
+    fl.Scan.select(w, d_packed, ref, bitmap, offsets, out)
+    values = oracle.unfor_pack(packed, ref, w, n_blocks=n)
+    want = values[(values >= lo) & (values <= hi)]
+    assert total == want.size
+    assert np.array_equal(to_host(out, 32)[:total], want)
+
+
+@pytest.mark.parametrize("tb", [8, 16, 32, 64])
+def test_filter_host_path(fl, oracle, tb):
+    rng = np.random.default_rng(1100 + tb)
+    n = 300
+    fl.host_configure(chunk_blocks=64, n_streams=3)  # 5 chunks over 3 slots, last one ragged
+    try:
+        for w in (0, 3, tb // 2 + 1, tb):
+            packed = rand_bytes(rng, n * 128 * w, tb)
+            ref = int(rng.integers(0, 1 << min(tb, 62)))
+            values = oracle.unfor_pack(packed, ref, w, n_blocks=n)
+            lo, hi = int(mask(tb) // 5), int(mask(tb) // 5 * 3)
+            want, sel = expected_bitmap(values, lo, hi)
+            bitmap = np.zeros(n * 128, dtype=np.uint8)
+            counts = np.zeros(n, dtype=np.uint32)
+            fl.Scan.filter_range(w, packed, ref, lo, hi, bitmap, counts)
+            assert np.array_equal(bitmap, want), (tb, w)
+            assert np.array_equal(counts, sel.reshape(n, 1024).sum(1).astype(np.uint32))
+    finally:
+        fl.host_configure(0, 0)
+
+
+def test_scan_errors(fl):
+    import torch
+
+    p = torch.zeros(32 * 33, dtype=torch.int32, device="cuda")
+    b = torch.zeros(128, dtype=torch.uint8, device="cuda")
+    with pytest.raises(fl.FastLanesError) as e:
+        fl.Scan.filter_range(33, p, 0, 0, 1, b)
+    assert e.value.status == 1  # FL_ERR_WIDTH
+    with pytest.raises(fl.FastLanesError):
+        fl.Scan.filter_range(8, p[: 32 * 8], 0, 0, 1, b[:100])
+    # empty batch is a no-op
+    fl.Scan.filter_range(8, p[:0], 0, 0, 1, b[:0])

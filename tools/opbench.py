@@ -65,6 +65,27 @@ def main():
             if True:  # fused chains: same algorithmic bytes as undelta_pack / pack + bases
                 rec("undelta_pack_untranspose", w, 128 * (w + tb + 1), lambda: _lib.fn("fl_undelta_pack_untranspose", tb)(w, n, P, B, U, sp))
                 rec("transpose_delta_pack", w, 128 * (w + tb + 1), lambda: _lib.fn("fl_transpose_delta_pack", tb)(w, n, U, B, P, sp))
+        # fused scan: filter = decode + range predicate -> 128-byte bitmap + count per block;
+        # select = decode + compaction of the selected values (here ~25 % selected by a value-independent bitmap)
+        bm = torch.empty(n * 128, dtype=torch.uint8, device="cuda")
+        cnt = torch.empty(n, dtype=torch.int32, device="cuda")
+        full = (1 << tb) - 1
+        for w in widths:
+            lo, hi = ((1 << w) - 1) // 4, ((1 << w) - 1) // 2
+            rec("unpack_filter", w, 128 * w + 128 + 4,
+                lambda: _lib.fn("fl_unpack_filter", tb)(w, n, P, None, 0, lo, hi, bm.data_ptr(), cnt.data_ptr(), sp))
+        bm.view(torch.int32).random_(-(1 << 31), (1 << 31) - 1)
+        bm2 = bm.clone(); bm2.view(torch.int32).random_(-(1 << 31), (1 << 31) - 1)
+        bm &= bm2  # density 1/4
+        del bm2
+        c64 = torch.tensor([bin(i).count("1") for i in range(256)], dtype=torch.int64, device="cuda")[bm.long()].view(n, 128).sum(1)
+        offs = torch.cumsum(c64, 0) - c64
+        total = int(c64.sum().item())
+        sel_out = torch.empty(total + 16, dtype=TDT[tb], device="cuda")
+        for w in widths:
+            rec("unpack_select_25pct", w, 128 * w + 128 + 8 + (tb // 8) * 256,
+                lambda: _lib.fn("fl_unpack_select", tb)(w, n, P, None, 7, bm.data_ptr(), offs.data_ptr(), sel_out.data_ptr(), sp))
+        del bm, cnt, c64, offs, sel_out
         rec("delta", 0, 128 * (2 * tb + 1), lambda: _lib.fn("fl_delta", tb)(n, U, B, P, sp))
         rec("undelta", 0, 128 * (2 * tb + 1), lambda: _lib.fn("fl_undelta", tb)(n, U, B, P, sp))
         mn = torch.empty(n, dtype=TDT[tb], device="cuda"); mx = torch.empty(n, dtype=TDT[tb], device="cuda")
