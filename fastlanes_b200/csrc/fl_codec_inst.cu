@@ -3,8 +3,15 @@
 // transpose, 3 = fused scan kernels)
 // and builds the runtime-width dispatch tables: the `match width { W => ::<W>() }` of
 // src/bitpacking.rs:82-95, :115-128 in the reference.
+#include <cstdlib>
+#include <cstring>
+
 #include "fl_internal.h"
 #include "fl_kernels.cuh"
+
+#ifndef FLB_U8_ORIG_DEFAULT_SLICE
+#define FLB_U8_ORIG_DEFAULT_SLICE 0
+#endif
 #if FLB_PART == 3
 #include "fl_scan.cuh"
 #endif
@@ -29,6 +36,18 @@ using launch_fn = cudaError_t (*)(const LaunchArgs&);
     return unsigned((n_blocks * kSlicesPerBlock + kThreads - 1) / kThreads);
 }
 
+// u8 fused original-order chains: FLB_U8_ORIG=warp|slice selects the warp-block (shared tile) or the row-slice
+// (8-byte global accesses, no shared memory) kernel for A/B measurement; the default is the measured best.
+[[maybe_unused]] static inline bool u8_orig_slice() {
+    static const bool v = [] {
+        const char* e = std::getenv("FLB_U8_ORIG");
+        if (e && std::strcmp(e, "warp") == 0) return false;
+        if (e && std::strcmp(e, "slice") == 0) return true;
+        return FLB_U8_ORIG_DEFAULT_SLICE != 0;
+    }();
+    return v;
+}
+
 #if FLB_PART == 0
 template <class T, int W, int OP>
 static cudaError_t do_unpack(const LaunchArgs& a) {
@@ -40,6 +59,13 @@ static cudaError_t do_unpack(const LaunchArgs& a) {
             static_cast<const char*>(a.in), static_cast<char*>(a.out), a.n_blocks, static_cast<const T*>(a.refs),
             T(a.ref_scalar), static_cast<const char*>(a.base));
         return cudaGetLastError();
+    }
+    if constexpr (sizeof(T) == 1 && OP == UOP_DELTA_ORIG) {
+        if (u8_orig_slice()) {
+            undelta_orig_u8_slice_kernel<W><<<grid_for(a.n_blocks), kThreads, 0, a.stream>>>(
+                static_cast<const char*>(a.in), static_cast<char*>(a.out), a.n_blocks, static_cast<const char*>(a.base));
+            return cudaGetLastError();
+        }
     }
     // warp-block layout: one warp per 1024-value block (see fl_kernels.cuh)
     const unsigned grid = unsigned((a.n_blocks * 32 + kThreads - 1) / kThreads);
@@ -87,6 +113,13 @@ cudaError_t launch_unpack<elem_t>(int op, const LaunchArgs& a) {
 #elif FLB_PART == 1
 template <class T, int W, int OP>
 static cudaError_t do_pack(const LaunchArgs& a) {
+    if constexpr (sizeof(T) == 1 && OP == POP_ORIG_DELTA) {
+        if (u8_orig_slice()) {
+            orig_delta_pack_u8_slice_kernel<W><<<grid_for(a.n_blocks), kThreads, 0, a.stream>>>(
+                static_cast<const char*>(a.in), static_cast<char*>(a.out), a.n_blocks, static_cast<const char*>(a.base));
+            return cudaGetLastError();
+        }
+    }
     const unsigned grid = unsigned((a.n_blocks * 32 + kThreads - 1) / kThreads);  // warp-block layout
     // Every variant stages one block per warp in dynamic shared memory: the original-order op as its swizzled tile,
     // the plain / FoR ops as the landing buffer of the TMA bulk load (+3..7% measured, profiles/kbench_r01_tma_pack_u32.txt).

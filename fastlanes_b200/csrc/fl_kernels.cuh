@@ -847,4 +847,131 @@ delta_kernel(const char* __restrict__ in, const char* __restrict__ base, char* _
     });
 }
 
+// ---------------------------------------------------------------------------------------------------
+// u8 fused original-order chains, ROW-SLICE layout (SURVEY.md §8f rank 1, u8 only).
+// A u8 block is 1 KiB: in the warp-block layout a thread holds only 2 rows, the 4-group shuffle scan and the
+// 16 STS.U16 + drain of the shared tile dominate (4.6-5.5 TB/s at W < 8).  With 8 threads per block a thread
+// holds ALL 8 rows of its 16 lanes, so (i) the delta chain is a register chain (no shuffles) and (ii) for every
+// lane the 8 rows are the 8 CONSECUTIVE originals start(l) .. start(l)+7, start(l) = 64*(l%16) + 8*FL_ORDER[l/16]
+// (src/transpose.rs:29-36 composed with src/macros.rs:20-24): one 8-byte global access per lane, assembled by
+// 4x4 byte transposes (PRMT).  Thread j owns lanes 16j+k: address 64*k + 8*FL_ORDER[j]; for a fixed k the 8 threads
+// of a block cover 64 contiguous bytes (two full sectors), a warp instruction four such segments.  No shared memory.
+// ---------------------------------------------------------------------------------------------------
+// o[b] = (a0.byte b, a1.byte b, a2.byte b, a3.byte b): 4x4 byte transpose, an involution
+__device__ __forceinline__ void byte_transpose4(uint32_t a0, uint32_t a1, uint32_t a2, uint32_t a3, uint32_t (&o)[4]) {
+    const uint32_t t0 = __byte_perm(a0, a1, 0x5140u), t1 = __byte_perm(a2, a3, 0x5140u);
+    const uint32_t t2 = __byte_perm(a0, a1, 0x7362u), t3 = __byte_perm(a2, a3, 0x7362u);
+    o[0] = __byte_perm(t0, t1, 0x5410u);
+    o[1] = __byte_perm(t0, t1, 0x7632u);
+    o[2] = __byte_perm(t2, t3, 0x5410u);
+    o[3] = __byte_perm(t2, t3, 0x7632u);
+}
+__device__ __forceinline__ void stg64_stream(void* p, uint32_t x, uint32_t y) {
+    asm volatile("st.global.cs.v2.u32 [%0], {%1,%2};" ::"l"(p), "r"(x), "r"(y) : "memory");
+}
+__device__ __forceinline__ uint2 ldg64_stream(const void* p) {
+    uint2 v;
+    asm volatile("ld.global.nc.L1::no_allocate.v2.u32 {%0,%1}, [%2];" : "=r"(v.x), "=r"(v.y) : "l"(p));
+    return v;
+}
+
+// untranspose(undelta_pack::<W>(packed, base)) for u8  (src/delta.rs:48-63 then src/transpose.rs:18-22)
+template <int W>
+__global__ void __launch_bounds__(kThreads)
+undelta_orig_u8_slice_kernel(const char* __restrict__ packed, char* __restrict__ out, size_t n_blocks,
+                             const char* __restrict__ base) {
+    using T = uint8_t;
+    const size_t tid = size_t(blockIdx.x) * kThreads + threadIdx.x;
+    const size_t blk = tid / kSlicesPerBlock;
+    const int j = int(tid % kSlicesPerBlock);
+    if (blk >= n_blocks) return;
+    Slice<T> prev = load_slice<T>(base + blk * 128 + j * 16);  // delta.rs:50
+    const char* pk = packed + blk * (size_t(128) * W) + j * 16;
+    Slice<T> w[W > 0 ? W : 1];
+    seq_rows<W>([&](auto kc) {
+        constexpr int k = decltype(kc)::value;
+        w[k] = load_slice<T>(pk + k * 128);
+    });
+    Slice<T> v[8];
+    seq_rows<8>([&](auto rc) {
+        constexpr int row = decltype(rc)::value;
+        Slice<T> x;
+        if constexpr (W == 0) x = slice_zero<T>();       // macros.rs:118-125
+        else if constexpr (W == 8) x = w[row];            // macros.rs:126-132
+        else {
+            constexpr int curr = (row * W) / 8;
+            constexpr int nxt = (curr + 1 < W) ? curr + 1 : curr;
+            x = extract_row<T, W, row>(w[curr], w[nxt]);
+        }
+        prev = slice_add<T>(prev, x);  // delta.rs:58-60
+        v[row] = prev;
+    });
+    char* ob = out + blk * 1024 + 8 * fl_order_rt(j);
+#pragma unroll
+    for (int r = 0; r < 4; ++r) {
+        uint32_t lo[4], hi[4];
+        byte_transpose4(v[0].r[r], v[1].r[r], v[2].r[r], v[3].r[r], lo);  // lane 4r+b: rows 0..3
+        byte_transpose4(v[4].r[r], v[5].r[r], v[6].r[r], v[7].r[r], hi);  // lane 4r+b: rows 4..7
+#pragma unroll
+        for (int b = 0; b < 4; ++b) stg64_stream(ob + 64 * (4 * r + b), lo[b], hi[b]);
+    }
+}
+
+// pack::<W>(delta(transpose(in), base)) for u8  (src/transpose.rs:11-15, src/delta.rs:24-33, src/macros.rs:35-97)
+template <int W>
+__global__ void __launch_bounds__(kThreads)
+orig_delta_pack_u8_slice_kernel(const char* __restrict__ in, char* __restrict__ packed, size_t n_blocks,
+                                const char* __restrict__ base) {
+    using T = uint8_t;
+    using R = uint32_t;
+    if constexpr (W == 0) return;  // macros.rs:52
+    const size_t tid = size_t(blockIdx.x) * kThreads + threadIdx.x;
+    const size_t blk = tid / kSlicesPerBlock;
+    const int j = int(tid % kSlicesPerBlock);
+    if (blk >= n_blocks) return;
+    Slice<T> prev = load_slice<T>(base + blk * 128 + j * 16);  // delta.rs:26
+    const char* ib = in + blk * 1024 + 8 * fl_order_rt(j);
+    uint2 c[16];
+#pragma unroll
+    for (int k = 0; k < 16; ++k) c[k] = ldg64_stream(ib + 64 * k);
+    Slice<T> v[8];
+#pragma unroll
+    for (int r = 0; r < 4; ++r) {
+        uint32_t lo[4], hi[4];
+        byte_transpose4(c[4 * r].x, c[4 * r + 1].x, c[4 * r + 2].x, c[4 * r + 3].x, lo);  // rows 0..3 of lanes 4r..4r+3
+        byte_transpose4(c[4 * r].y, c[4 * r + 1].y, c[4 * r + 2].y, c[4 * r + 3].y, hi);  // rows 4..7
+#pragma unroll
+        for (int b = 0; b < 4; ++b) { v[b].r[r] = lo[b]; v[4 + b].r[r] = hi[b]; }
+    }
+    char* pk = packed + blk * (size_t(128) * W) + j * 16;
+    Slice<T> tmp = slice_zero<T>();
+    seq_rows<8>([&](auto rc) {
+        constexpr int row = decltype(rc)::value;
+        Slice<T> s = slice_sub<T>(v[row], prev);  // delta.rs:28-30
+        prev = v[row];
+        if constexpr (W == 8) {
+            store_slice<T>(pk + row * 128, s);  // macros.rs:54-59
+        } else {
+            constexpr int shift = (row * W) % 8;
+            constexpr int curr = (row * W) / 8;
+            constexpr int next = ((row + 1) * W) / 8;
+            constexpr R MW = rep_mask<T>(W);
+#pragma unroll
+            for (int i = 0; i < 4; ++i) {
+                const R x = s.r[i] & MW;  // macros.rs:73
+                if constexpr (shift == 0) tmp.r[i] = x;
+                else if constexpr (shift + W <= 8) tmp.r[i] |= x << shift;
+                else tmp.r[i] |= lane_shl<T, shift>(x);  // macros.rs:79
+                s.r[i] = x;
+            }
+            if constexpr (next > curr) {  // macros.rs:88-92
+                store_slice<T>(pk + curr * 128, tmp);
+                constexpr int rem = ((row + 1) * W) % 8;
+#pragma unroll
+                for (int i = 0; i < 4; ++i) tmp.r[i] = lane_shr_keep<T, W - rem, rem>(s.r[i]);
+            }
+        }
+    });
+}
+
 }  // namespace flb

@@ -21,21 +21,34 @@
 
 namespace flb {
 
-// predicate bits of one 16-byte slice: bit k = lane k passes  (v - c) <= span  (lane-wise, wrapping, unsigned)
-template <class T>
-__device__ __forceinline__ uint32_t slice_range_bits(const Slice<T>& v, typename Lay<T>::R c, typename Lay<T>::R span) {
-    uint32_t b = 0;
+// Predicate bits of one 16-byte slice, ORed into `acc` at bit position POS: bit POS+k = lane k passes
+// (v - c) <= span  (lane-wise, wrapping, unsigned).  spanH = span | H for the SWAR types.
+template <class T, int POS>
+__device__ __forceinline__ void slice_range_bits(uint32_t& acc, const Slice<T>& v, typename Lay<T>::R c,
+                                                 typename Lay<T>::R span, typename Lay<T>::R spanH) {
     if constexpr (sizeof(T) >= 4) {
-#pragma unroll
-        for (int r = 0; r < Lay<T>::NR; ++r) b |= uint32_t((v.r[r] - c) <= span) << r;
+        // one lane per register: handled by shift_in_fail() in the kernel (carry chain), not here
+        static_assert(sizeof(T) < 4, "u32/u64 use shift_in_fail");
     } else if constexpr (sizeof(T) == 2) {
 #pragma unroll
-        for (int r = 0; r < 4; ++r) b |= mask_halves_to_bits(__vcmpleu2(__vsub2(v.r[r], c), span)) << (2 * r);
+        for (int r = 0; r < 4; ++r) {
+            acc |= top_bits_u16(swar_leu_top<16>(lane_sub<T>(v.r[r], c), span, spanH)) << (POS + 2 * r);
+        }
     } else {
 #pragma unroll
-        for (int r = 0; r < 4; ++r) b |= mask_bytes_to_bits(__vcmpleu4(__vsub4(v.r[r], c), span)) << (4 * r);
+        for (int r = 0; r < 4; ++r) {
+            acc |= top_bits_u8(swar_leu_top<8>(lane_sub<T>(v.r[r], c), span, spanH)) << (POS + 4 * r);
+        }
     }
-    return b;
+}
+
+// u32 / u64 (one lane per register): acc = 2*acc + (t > span), as a borrow chain — SUB sets the carry flag to the
+// borrow of span - t, ADDC shifts it into acc: two instructions per value, no predicate / select / shift-or.
+__device__ __forceinline__ void shift_in_fail(uint32_t& acc, uint32_t t, uint32_t span) {
+    asm("{\n .reg .u32 d;\n sub.cc.u32 d, %1, %2;\n addc.u32 %0, %0, %0;\n}" : "+r"(acc) : "r"(span), "r"(t));
+}
+__device__ __forceinline__ void shift_in_fail(uint32_t& acc, uint64_t t, uint64_t span) {
+    asm("{\n .reg .u64 d;\n sub.cc.u64 d, %1, %2;\n addc.u32 %0, %0, %0;\n}" : "+r"(acc) : "l"(span), "l"(t));
 }
 
 template <class T, int W, bool TMA>
@@ -59,9 +72,22 @@ filter_warp_kernel(const char* __restrict__ packed, unsigned char* __restrict__ 
     // value = v + ref (ffor.rs:47, wrapping).  lo <= value <= hi  <=>  (v - (lo - ref)) mod 2^T <= hi - lo
     const Slice<T> cs = slice_splat<T>(T(lo - ref)), ss = slice_splat<T>(T(hi - lo));
     const R c = cs.r[0], span = ss.r[0];
+    R spanH = span;
+    if constexpr (sizeof(T) <= 2) spanH = span | rep_value<T>(T(T(1) << (TB - 1)));
     uint32_t x = 0;
+    if constexpr (sizeof(T) >= 4) {
+        // values in DESCENDING bit position (row RPG-1 first): the last one shifted in lands at bit 0
 #pragma unroll
-    for (int i = 0; i < RPG; ++i) x |= slice_range_bits<T>(v[i], c, span) << (i * BPT);
+        for (int i = RPG - 1; i >= 0; --i)
+#pragma unroll
+            for (int r = Lay<T>::NR - 1; r >= 0; --r) shift_in_fail(x, R(v[i].r[r] - c), span);
+        x = ~x;  // fail bits -> pass bits  (RPG * NR == 32 values: every bit of x is one value)
+    } else {
+        seq_rows<RPG>([&](auto ic) {
+            constexpr int i = decltype(ic)::value;
+            slice_range_bits<T, i * BPT>(x, v[i], c, span, spanH);
+        });
+    }
     if (hi < lo) x = 0;  // empty range
 
     __shared__ __align__(16) unsigned char scan_tile[kThreads / 32][128];

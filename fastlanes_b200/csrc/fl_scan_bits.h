@@ -59,11 +59,21 @@ FLB_HD uint32_t merge_quad_bpt2(uint32_t mine, uint32_t other, int j) {
     return spread4((lo >> (16 * h)) & 0xFFFFu) | (spread4((hi >> (16 * h)) & 0xFFFFu) << 4);
 }
 
-// SWAR comparison masks -> packed predicate bits
-// u8: m holds 0xFF / 0x00 per byte -> 4 bits (bit k = byte k)
-FLB_HD uint32_t mask_bytes_to_bits(uint32_t m) { return ((m & 0x08040201u) * 0x01010101u) >> 24; }
-// u16: m holds 0xFFFF / 0x0000 per half -> 2 bits
-FLB_HD uint32_t mask_halves_to_bits(uint32_t m) { return ((m & 0x00020001u) * 0x00010001u) >> 16; }
+// Lane-wise unsigned "x <= y" on the SWAR lanes of a 32-bit register (TBITS = 8: 4 lanes, 16: 2 lanes); the
+// result is the TOP bit of every lane.  yH = y | H (H = top bit of every lane).  d = (y|H) - (x&~H) never borrows
+// across lanes and its top bit says low(y) >= low(x); the top bits of x and y decide otherwise (one LOP3 on the GPU).
+template <int TBITS>
+FLB_HD uint32_t swar_leu_top(uint32_t x, uint32_t y, uint32_t yH) {
+    const uint32_t H = (TBITS == 8) ? 0x80808080u : 0x80008000u;
+    const uint32_t d = yH - (x & ~H);
+    return ((~x & y) | (~(x ^ y) & d)) & H;
+}
+// top bits of the lanes -> packed predicate bits (bit k = lane k)
+FLB_HD uint32_t top_bits_u8(uint32_t le) { return ((((le >> 7) & 0x01010101u) * 0x00204081u) >> 21) & 15u; }
+FLB_HD uint32_t top_bits_u16(uint32_t le) {
+    const uint32_t m = le >> 15;  // bit 0, bit 16
+    return (m | (m >> 15)) & 3u;
+}
 
 // Stores a thread's assembled word into the warp's 128-byte bitmap tile.  `z` is, per element size:
 //   u8  : X itself                (2 rows x 16 lanes: two 16-bit stores)

@@ -68,16 +68,32 @@ static int run(int trials) {
 
 int main() {
     int bad = 0;
-    // mask -> bits helpers
-    for (int m = 0; m < 16; ++m) {
-        uint32_t w = 0;
-        for (int k = 0; k < 4; ++k) if (m >> k & 1) w |= 0xFFu << (8 * k);
-        if (flb::mask_bytes_to_bits(w) != (uint32_t)m) { std::printf("mask_bytes_to_bits(%08x)\n", w); ++bad; }
-    }
-    for (int m = 0; m < 4; ++m) {
-        uint32_t w = 0;
-        for (int k = 0; k < 2; ++k) if (m >> k & 1) w |= 0xFFFFu << (16 * k);
-        if (flb::mask_halves_to_bits(w) != (uint32_t)m) { std::printf("mask_halves_to_bits(%08x)\n", w); ++bad; }
+    // SWAR lane-wise x <= y and the top-bit compression: u8 exhaustive over (x, y) in every lane position with
+    // random neighbours; u16 edge values x random
+    for (int x = 0; x < 256; ++x)
+        for (int y = 0; y < 256; ++y) {
+            const uint32_t nx = (uint32_t)rnd(), ny = (uint32_t)rnd();
+            for (int k = 0; k < 4; ++k) {
+                const uint32_t X = (nx & ~(0xFFu << (8 * k))) | ((uint32_t)x << (8 * k));
+                const uint32_t Y = (ny & ~(0xFFu << (8 * k))) | ((uint32_t)y << (8 * k));
+                const uint32_t bits = flb::top_bits_u8(flb::swar_leu_top<8>(X, Y, Y | 0x80808080u));
+                uint32_t want = 0;
+                for (int l = 0; l < 4; ++l) if (((X >> (8 * l)) & 0xFF) <= ((Y >> (8 * l)) & 0xFF)) want |= 1u << l;
+                if (bits != want) { if (bad < 5) std::printf("u8 leu X=%08x Y=%08x got %x want %x\n", X, Y, bits, want); ++bad; }
+            }
+        }
+    {
+        const uint32_t edge[] = {0, 1, 2, 0x7FFE, 0x7FFF, 0x8000, 0x8001, 0xFFFE, 0xFFFF, 0x1234, 0xABCD};
+        for (int t = 0; t < 200000; ++t) {
+            uint32_t X = (uint32_t)rnd(), Y = (uint32_t)rnd();
+            if (t % 3 == 0) X = (X & 0xFFFF0000u) | edge[rnd() % 11];
+            if (t % 5 == 0) Y = (Y & 0x0000FFFFu) | (edge[rnd() % 11] << 16);
+            if (t % 7 == 0) Y = X;
+            if (t % 11 == 0) X = (X & 0xFFFFu) | (Y & 0xFFFF0000u);
+            const uint32_t bits = flb::top_bits_u16(flb::swar_leu_top<16>(X, Y, Y | 0x80008000u));
+            const uint32_t want = uint32_t((X & 0xFFFF) <= (Y & 0xFFFF)) | (uint32_t((X >> 16) <= (Y >> 16)) << 1);
+            if (bits != want) { if (bad < 5) std::printf("u16 leu X=%08x Y=%08x got %x want %x\n", X, Y, bits, want); ++bad; }
+        }
     }
     bad += run<8>(200);
     bad += run<16>(200);

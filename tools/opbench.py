@@ -29,11 +29,16 @@ def timeit(fn, iters=7):
 
 
 def main():
-    only = set(sys.argv[1].split(",")) if len(sys.argv) > 1 else None  # e.g. "transpose,untranspose"
+    args = [a for a in sys.argv[1:] if not a.startswith("--")]
+    only = set(args[0].split(",")) if args else None  # e.g. "transpose,untranspose"
+    types = (8, 16, 32, 64)
+    if "--types" in sys.argv:  # e.g. --types 8,16
+        types = tuple(int(t) for t in sys.argv[sys.argv.index("--types") + 1].split(","))
+        only = set(sys.argv[1].split(",")) if not sys.argv[1].startswith("--") else None
     lg_bytes = 32  # 4 GiB unpacked per type
     rows = []
     sp = torch.cuda.current_stream().cuda_stream
-    for tb in (8, 16, 32, 64):
+    for tb in types:
         n = (1 << lg_bytes) // (128 * tb)
         unp = torch.empty(n * 1024, dtype=TDT[tb], device="cuda")
         unp.view(torch.int32).random_(-(1 << 31), (1 << 31) - 1)
@@ -67,25 +72,25 @@ def main():
                 rec("transpose_delta_pack", w, 128 * (w + tb + 1), lambda: _lib.fn("fl_transpose_delta_pack", tb)(w, n, U, B, P, sp))
         # fused scan: filter = decode + range predicate -> 128-byte bitmap + count per block;
         # select = decode + compaction of the selected values (here ~25 % selected by a value-independent bitmap)
-        bm = torch.empty(n * 128, dtype=torch.uint8, device="cuda")
-        cnt = torch.empty(n, dtype=torch.int32, device="cuda")
-        full = (1 << tb) - 1
-        for w in widths:
-            lo, hi = ((1 << w) - 1) // 4, ((1 << w) - 1) // 2
-            rec("unpack_filter", w, 128 * w + 128 + 4,
-                lambda: _lib.fn("fl_unpack_filter", tb)(w, n, P, None, 0, lo, hi, bm.data_ptr(), cnt.data_ptr(), sp))
-        bm.view(torch.int32).random_(-(1 << 31), (1 << 31) - 1)
-        bm2 = bm.clone(); bm2.view(torch.int32).random_(-(1 << 31), (1 << 31) - 1)
-        bm &= bm2  # density 1/4
-        del bm2
-        c64 = torch.tensor([bin(i).count("1") for i in range(256)], dtype=torch.int64, device="cuda")[bm.long()].view(n, 128).sum(1)
-        offs = torch.cumsum(c64, 0) - c64
-        total = int(c64.sum().item())
-        sel_out = torch.empty(total + 16, dtype=TDT[tb], device="cuda")
-        for w in widths:
-            rec("unpack_select_25pct", w, 128 * w + 128 + 8 + (tb // 8) * 256,
-                lambda: _lib.fn("fl_unpack_select", tb)(w, n, P, None, 7, bm.data_ptr(), offs.data_ptr(), sel_out.data_ptr(), sp))
-        del bm, cnt, c64, offs, sel_out
+        if not only or (only & {"unpack_filter", "unpack_select_25pct"}):
+            bm = torch.empty(n * 128, dtype=torch.uint8, device="cuda")
+            cnt = torch.empty(n, dtype=torch.int32, device="cuda")
+            for w in widths:
+                lo, hi = ((1 << w) - 1) // 4, ((1 << w) - 1) // 2
+                rec("unpack_filter", w, 128 * w + 128 + 4,
+                    lambda: _lib.fn("fl_unpack_filter", tb)(w, n, P, None, 0, lo, hi, bm.data_ptr(), cnt.data_ptr(), sp))
+            bm.view(torch.int32).random_(-(1 << 31), (1 << 31) - 1)
+            bm2 = bm.clone(); bm2.view(torch.int32).random_(-(1 << 31), (1 << 31) - 1)
+            bm &= bm2  # density 1/4
+            del bm2
+            c64 = torch.tensor([bin(i).count("1") for i in range(256)], dtype=torch.int64, device="cuda")[bm.long()].view(n, 128).sum(1)
+            offs = torch.cumsum(c64, 0) - c64
+            total = int(c64.sum().item())
+            sel_out = torch.empty(total + 16, dtype=TDT[tb], device="cuda")
+            for w in widths:
+                rec("unpack_select_25pct", w, 128 * w + 128 + 8 + (tb // 8) * 256,
+                    lambda: _lib.fn("fl_unpack_select", tb)(w, n, P, None, 7, bm.data_ptr(), offs.data_ptr(), sel_out.data_ptr(), sp))
+            del bm, cnt, c64, offs, sel_out
         rec("delta", 0, 128 * (2 * tb + 1), lambda: _lib.fn("fl_delta", tb)(n, U, B, P, sp))
         rec("undelta", 0, 128 * (2 * tb + 1), lambda: _lib.fn("fl_undelta", tb)(n, U, B, P, sp))
         mn = torch.empty(n, dtype=TDT[tb], device="cuda"); mx = torch.empty(n, dtype=TDT[tb], device="cuda")
