@@ -42,13 +42,15 @@ __device__ __forceinline__ void slice_range_bits(uint32_t& acc, const Slice<T>& 
     }
 }
 
-// u32 / u64 (one lane per register): acc = 2*acc + (t > span), as a borrow chain — SUB sets the carry flag to the
-// borrow of span - t, ADDC shifts it into acc: two instructions per value, no predicate / select / shift-or.
-__device__ __forceinline__ void shift_in_fail(uint32_t& acc, uint32_t t, uint32_t span) {
-    asm("{\n .reg .u32 d;\n sub.cc.u32 d, %1, %2;\n addc.u32 %0, %0, %0;\n}" : "+r"(acc) : "r"(span), "r"(t));
+// u32 / u64 (one lane per register): acc = 2*acc + (t > span) as a carry chain.  t > span  <=>  t + ~span carries out
+// of the register, so ADD.CC sets the carry flag to "fail" and ADDC shifts it into acc: two instructions per value,
+// no predicate / select / shift-or.  (ADD, not SUB: the carry of an addition is unambiguous, whereas after sub.cc the
+// flag read by addc is the hardware carry = NOT borrow.)
+__device__ __forceinline__ void shift_in_fail(uint32_t& acc, uint32_t t, uint32_t not_span) {
+    asm("{\n .reg .u32 d;\n add.cc.u32 d, %1, %2;\n addc.u32 %0, %0, %0;\n}" : "+r"(acc) : "r"(t), "r"(not_span));
 }
-__device__ __forceinline__ void shift_in_fail(uint32_t& acc, uint64_t t, uint64_t span) {
-    asm("{\n .reg .u64 d;\n sub.cc.u64 d, %1, %2;\n addc.u32 %0, %0, %0;\n}" : "+r"(acc) : "l"(span), "l"(t));
+__device__ __forceinline__ void shift_in_fail(uint32_t& acc, uint64_t t, uint64_t not_span) {
+    asm("{\n .reg .u64 d;\n add.cc.u64 d, %1, %2;\n addc.u32 %0, %0, %0;\n}" : "+r"(acc) : "l"(t), "l"(not_span));
 }
 
 template <class T, int W, bool TMA>
@@ -77,10 +79,11 @@ filter_warp_kernel(const char* __restrict__ packed, unsigned char* __restrict__ 
     uint32_t x = 0;
     if constexpr (sizeof(T) >= 4) {
         // values in DESCENDING bit position (row RPG-1 first): the last one shifted in lands at bit 0
+        const R not_span = ~span;
 #pragma unroll
         for (int i = RPG - 1; i >= 0; --i)
 #pragma unroll
-            for (int r = Lay<T>::NR - 1; r >= 0; --r) shift_in_fail(x, R(v[i].r[r] - c), span);
+            for (int r = Lay<T>::NR - 1; r >= 0; --r) shift_in_fail(x, R(v[i].r[r] - c), not_span);
         x = ~x;  // fail bits -> pass bits  (RPG * NR == 32 values: every bit of x is one value)
     } else {
         seq_rows<RPG>([&](auto ic) {

@@ -83,19 +83,23 @@ FLB_HD uint32_t top_bits_u16(uint32_t le) {
 // q = rank of the thread's group in row order (rows q*RPG .. q*RPG + RPG-1), j = slice index 0..7.
 template <int TBITS>
 FLB_HD void scan_store(unsigned char* tile, int q, int j, uint32_t z) {
-    if (TBITS == 8) {
+    // The 4 (u8: 2) rows a thread stores never cross a multiple of 8, so FL_ORDER[r/8] is common to them and
+    // consecutive rows are 16 bytes apart (row_bitmap_byte): one base address, immediate offsets.
+    if (TBITS == 8) {        // rows 2q + i
+        unsigned char* p = tile + row_bitmap_byte(2 * q) + 2 * j;
         for (int i = 0; i < 2; ++i) {
-            unsigned char* p = tile + row_bitmap_byte(q * 2 + i) + 2 * j;
-            p[0] = (unsigned char)(z >> (16 * i));
-            p[1] = (unsigned char)(z >> (16 * i + 8));
+            p[16 * i] = (unsigned char)(z >> (16 * i));
+            p[16 * i + 1] = (unsigned char)(z >> (16 * i + 8));
         }
-    } else if (TBITS == 16) {
-        for (int i = 0; i < 4; ++i) tile[row_bitmap_byte(q * 4 + i) + j] = (unsigned char)(z >> (8 * i));
-    } else if (TBITS == 32) {
-        for (int ii = 0; ii < 4; ++ii) tile[row_bitmap_byte(q * 8 + 4 * (j & 1) + ii) + (j >> 1)] = (unsigned char)(z >> (8 * ii));
-    } else {
-        for (int ii = 0; ii < 4; ++ii)
-            tile[row_bitmap_byte(q * 16 + 8 * (j & 1) + 4 * ((j >> 1) & 1) + ii) + (j >> 2)] = (unsigned char)(z >> (8 * ii));
+    } else if (TBITS == 16) {  // rows 4q + i
+        unsigned char* p = tile + row_bitmap_byte(4 * q) + j;
+        for (int i = 0; i < 4; ++i) p[16 * i] = (unsigned char)(z >> (8 * i));
+    } else if (TBITS == 32) {  // rows 8q + 4(j&1) + ii
+        unsigned char* p = tile + row_bitmap_byte(8 * q + 4 * (j & 1)) + (j >> 1);
+        for (int ii = 0; ii < 4; ++ii) p[16 * ii] = (unsigned char)(z >> (8 * ii));
+    } else {                   // rows 16q + 8(j&1) + 4((j>>1)&1) + ii
+        unsigned char* p = tile + row_bitmap_byte(16 * q + 8 * (j & 1) + 4 * ((j >> 1) & 1)) + (j >> 2);
+        for (int ii = 0; ii < 4; ++ii) p[16 * ii] = (unsigned char)(z >> (8 * ii));
     }
 }
 
