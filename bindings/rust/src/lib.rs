@@ -190,8 +190,36 @@ pub mod device {
         pub fn fl_undelta_pack_u32(width: u32, n_blocks: usize, packed: *const u32, base: *const u32, out: *mut u32, stream: *mut c_void) -> i32;
         pub fn fl_unpack_gather_u32(width: u32, n_blocks: usize, packed: *const u32, global_index: *const u64, n: usize,
                                     out: *mut u32, oob_flag: *mut i32, stream: *mut c_void) -> i32;
+        /// Fused scan (not in the reference: `unfor_pack` + the caller-side predicate loop of README.md:40-41 in one
+        /// pass).  bitmap: 128 bytes per block, bit i = lo <= unfor_pack(packed, reference)[i] <= hi; counts nullable.
+        pub fn fl_unpack_filter_u32(width: u32, n_blocks: usize, packed: *const u32, refs: *const u32, reference: u32,
+                                    lo: u32, hi: u32, bitmap: *mut u8, counts: *mut u32, stream: *mut c_void) -> i32;
+        /// Dense compaction of the selected values: out[offsets[b] + k] = k-th selected value of block b.
+        pub fn fl_unpack_select_u32(width: u32, n_blocks: usize, packed: *const u32, refs: *const u32, reference: u32,
+                                    bitmap: *const u8, offsets: *const u64, out: *mut u32, stream: *mut c_void) -> i32;
         // ... the same set exists for u8 / u16 / u64 and for pack / for_pack / delta / undelta / (un)transpose:
         // see include/fastlanes_b200.h (FL_DECLARE_TYPE).
+    }
+}
+
+/// Host-slice scan: `FoR::unfor_pack::<W>` + range predicate over a batch of packed blocks; the decoded values never
+/// leave the GPU, only the selection bitmap (128 bytes per block) and the per-block counts come back.
+pub mod scan {
+    extern "C" {
+        fn fl_host_unpack_filter_u32(width: u32, n_blocks: usize, packed: *const u32, reference: u32, lo: u32, hi: u32,
+                                     bitmap: *mut u8, counts: *mut u32) -> i32;
+    }
+    pub fn filter_range_u32(width: usize, packed: &[u32], reference: u32, lo: u32, hi: u32, bitmap: &mut [u8],
+                            counts: Option<&mut [u32]>) {
+        let n_blocks = bitmap.len() / 128;
+        assert_eq!(bitmap.len(), n_blocks * 128);
+        assert_eq!(packed.len(), n_blocks * 32 * width);
+        let c = match counts {
+            Some(c) => { assert_eq!(c.len(), n_blocks); c.as_mut_ptr() }
+            None => core::ptr::null_mut(),
+        };
+        super::check(unsafe { fl_host_unpack_filter_u32(width as u32, n_blocks, packed.as_ptr(), reference, lo, hi,
+                                                       bitmap.as_mut_ptr(), c) }, "unpack_filter");
     }
 }
 

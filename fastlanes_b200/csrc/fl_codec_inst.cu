@@ -9,9 +9,6 @@
 #include "fl_internal.h"
 #include "fl_kernels.cuh"
 
-#ifndef FLB_FILTER_TMA_DEFAULT
-#define FLB_FILTER_TMA_DEFAULT 1
-#endif
 #ifndef FLB_U8_ORIG_DEFAULT_SLICE
 #define FLB_U8_ORIG_DEFAULT_SLICE 1  // measured: 6.5-7.1 TB/s vs 4.6-6.4 (profiles/opbench_u8orig_r01.txt)
 #endif
@@ -157,24 +154,16 @@ cudaError_t launch_pack<elem_t>(int op, const LaunchArgs& a) {
     return cudaErrorNotSupported;
 }
 #elif FLB_PART == 3
-// fused decode + predicate kernels (fl_scan.cuh); same load-path choice as the plain unpack (TMA for u16/u32/u64)
+// fused decode + predicate kernels (fl_scan.cuh)
 template <class T, int W>
 static cudaError_t do_filter(const LaunchArgs& a) {
     const unsigned grid = unsigned((a.n_blocks * 32 + kThreads - 1) / kThreads);
-    // FLB_FILTER_TMA=0|1: direct loads vs the TMA bulk load of the packed block (A/B measurement; u8 is always direct)
-    static const bool tma = [] {
-        const char* e = std::getenv("FLB_FILTER_TMA");
-        return e ? (e[0] != '0') : (FLB_FILTER_TMA_DEFAULT != 0);
-    }();
-    if (sizeof(T) >= 2 && tma) {
-        filter_warp_kernel<T, W, (sizeof(T) >= 2)><<<grid, kThreads, 0, a.stream>>>(
-            static_cast<const char*>(a.in), static_cast<unsigned char*>(a.out), a.counts, a.n_blocks,
-            static_cast<const T*>(a.refs), T(a.ref_scalar), T(a.flo), T(a.fhi));
-    } else {
-        filter_warp_kernel<T, W, false><<<grid, kThreads, 0, a.stream>>>(
-            static_cast<const char*>(a.in), static_cast<unsigned char*>(a.out), a.counts, a.n_blocks,
-            static_cast<const T*>(a.refs), T(a.ref_scalar), T(a.flo), T(a.fhi));
-    }
+    // Direct 128-bit loads, not the TMA bulk load: the filter reads little per block and is ALU-bound below W ~ 3T/4,
+    // where the mbarrier round trip costs 10-15 % (u32 W=8: 300 vs 346 us; equal at W >= 29 —
+    // profiles/opbench_filter_tma_r01.txt).
+    filter_warp_kernel<T, W, false><<<grid, kThreads, 0, a.stream>>>(
+        static_cast<const char*>(a.in), static_cast<unsigned char*>(a.out), a.counts, a.n_blocks,
+        static_cast<const T*>(a.refs), T(a.ref_scalar), T(a.flo), T(a.fhi));
     return cudaGetLastError();
 }
 template <class T, int W>

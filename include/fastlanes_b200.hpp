@@ -43,6 +43,7 @@ template <class T> struct Abi;
         static fl_status undelta_pack(unsigned w, size_t n, const T* i, const T* b, T* o) { return fl_host_undelta_pack_##SFX(w, n, i, b, o); } \
         static fl_status undelta_pack_untranspose(unsigned w, size_t n, const T* i, const T* b, T* o) { return fl_host_undelta_pack_untranspose_##SFX(w, n, i, b, o); } \
         static fl_status transpose_delta_pack(unsigned w, size_t n, const T* i, const T* b, T* o) { return fl_host_transpose_delta_pack_##SFX(w, n, i, b, o); } \
+        static fl_status filter(unsigned w, size_t n, const T* i, T r, T lo, T hi, uint8_t* bm, uint32_t* c) { return fl_host_unpack_filter_##SFX(w, n, i, r, lo, hi, bm, c); } \
         static fl_status transpose(size_t n, const T* i, T* o) { return fl_host_transpose_##SFX(n, i, o); }     \
         static fl_status untranspose(size_t n, const T* i, T* o) { return fl_host_untranspose_##SFX(n, i, o); } \
     };
@@ -134,6 +135,20 @@ struct Delta {
     template <std::size_t W>
     static void transpose_delta_pack(const std::array<T, 1024>& input, const Base& base, Packed<T, W>& output) {
         detail::check(detail::Abi<T>::transpose_delta_pack(W, 1, input.data(), base.data(), output.data()), "transpose_delta_pack");
+    }
+};
+
+// Fused scan (not a trait of the reference: FoR::unfor_pack + the caller-side loop of README.md:40-41 in one GPU
+// pass).  Returns the number of selected values; bit i of `bitmap` = lo <= unfor_pack::<W>(input, reference)[i] <= hi.
+template <class T>
+struct Scan {
+    using Bitmap = std::array<uint8_t, 128>;
+    template <std::size_t W>
+    static uint32_t filter_range(const Packed<T, W>& input, T reference, T lo, T hi, Bitmap& bitmap) {
+        static_assert(W <= FastLanes<T>::T_BITS, "BitPackWidth<W>: SupportedBitPackWidth<T>");
+        uint32_t count = 0;
+        detail::check(detail::Abi<T>::filter(W, 1, input.data(), reference, lo, hi, bitmap.data(), &count), "filter_range");
+        return count;
     }
 };
 

@@ -137,16 +137,18 @@ int flo_run(int tbits, int op, unsigned width, size_t n_blocks, const void* in, 
             const void* refs, uint64_t ref_scalar, int n_threads) {
     const int slot = type_slot(tbits);
     if (slot < 0) return FLO_ERR_TYPE;
-    if (op < FLO_OP_PACK || op > FLO_OP_UNTRANSPOSE) return FLO_ERR_TYPE;
+    if (op < FLO_OP_PACK || op > FLO_OP_UNFOR_FILTER) return FLO_ERR_TYPE;
     const bool width_op = (op == FLO_OP_PACK || op == FLO_OP_UNPACK || op == FLO_OP_FOR_PACK ||
-                           op == FLO_OP_UNFOR_PACK || op == FLO_OP_UNDELTA_PACK);
+                           op == FLO_OP_UNFOR_PACK || op == FLO_OP_UNDELTA_PACK || op == FLO_OP_UNFOR_FILTER);
     if (width_op && width > unsigned(tbits)) return FLO_ERR_WIDTH;  // bitpacking.rs:93,126
     if (!width_op) width = 0;
     if (n_blocks == 0) return FLO_OK;
-    const bool needs_in = !(width == 0 && (op == FLO_OP_UNPACK || op == FLO_OP_UNFOR_PACK || op == FLO_OP_UNDELTA_PACK));
+    const bool needs_in = !(width == 0 && (op == FLO_OP_UNPACK || op == FLO_OP_UNFOR_PACK || op == FLO_OP_UNDELTA_PACK ||
+                                          op == FLO_OP_UNFOR_FILTER));
     const bool needs_out = !(width == 0 && (op == FLO_OP_PACK || op == FLO_OP_FOR_PACK));
     if ((needs_in && !in) || (needs_out && !out)) return FLO_ERR_NULL;
-    if ((op == FLO_OP_DELTA || op == FLO_OP_UNDELTA || op == FLO_OP_UNDELTA_PACK) && !base) return FLO_ERR_NULL;
+    if ((op == FLO_OP_DELTA || op == FLO_OP_UNDELTA || op == FLO_OP_UNDELTA_PACK || op == FLO_OP_UNFOR_FILTER) && !base)
+        return FLO_ERR_NULL;
     const run_fn run = tab().run[slot];
     if (n_threads <= 1 || n_blocks < 2) {
         run(op, width, 0, n_blocks, in, out, base, refs, ref_scalar);

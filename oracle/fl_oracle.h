@@ -37,7 +37,10 @@ enum {
     FLO_OP_UNDELTA = 5,      /* delta.rs:36-45  (width ignored) */
     FLO_OP_UNDELTA_PACK = 6, /* delta.rs:48-63 */
     FLO_OP_TRANSPOSE = 7,    /* transpose.rs:11-15 (width ignored) */
-    FLO_OP_UNTRANSPOSE = 8   /* transpose.rs:18-22 (width ignored) */
+    FLO_OP_UNTRANSPOSE = 8,  /* transpose.rs:18-22 (width ignored) */
+    FLO_OP_UNFOR_FILTER = 9  /* NOT a reference function: ffor.rs:38-50 into a 1024-value scratch + the caller-side
+                                range-predicate loop (README.md:40-41).  base = {lo, hi} (2 elements),
+                                out = bitmap, 128 bytes per block, bit i = lo <= value[i] <= hi */
 };
 
 /* Generic batched entry point.  base: n_blocks*LANES (delta ops), refs: per-block references or

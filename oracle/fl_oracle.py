@@ -17,7 +17,8 @@ import numpy as np
 _HERE = os.path.dirname(os.path.abspath(__file__))
 _LIB_PATH = os.path.join(_HERE, "_build", "libfl_oracle.so")
 
-OP_PACK, OP_UNPACK, OP_FOR_PACK, OP_UNFOR_PACK, OP_DELTA, OP_UNDELTA, OP_UNDELTA_PACK, OP_TRANSPOSE, OP_UNTRANSPOSE = range(9)
+OP_PACK, OP_UNPACK, OP_FOR_PACK, OP_UNFOR_PACK, OP_DELTA, OP_UNDELTA, OP_UNDELTA_PACK, OP_TRANSPOSE, OP_UNTRANSPOSE, \
+    OP_UNFOR_FILTER = range(10)
 
 FLO_OK, FLO_ERR_WIDTH, FLO_ERR_TYPE, FLO_ERR_INDEX, FLO_ERR_NULL = range(5)
 
@@ -218,6 +219,23 @@ def unpack_gather(packed: np.ndarray, width: int, global_index: np.ndarray) -> n
     rc = lib().flo_unpack_gather(tbits_of(packed), width, _ptr(packed), _ptr(gi), gi.size, _ptr(out))
     if rc != FLO_OK:
         raise OracleError(rc, "unpack_gather")
+    return out
+
+
+def unfor_filter(packed: np.ndarray, reference, width: int, lo: int, hi: int, n_blocks: int | None = None,
+                 threads: int = 1, out: np.ndarray | None = None) -> np.ndarray:
+    """NOT a reference function: `unfor_pack` (src/ffor.rs:38-50) into a per-block scratch buffer followed by the
+    caller-side predicate loop the reference's README prescribes (README.md:40-41).  Returns the selection bitmap,
+    128 bytes per block, bit i of a block = lo <= value[i] <= hi."""
+    packed = np.ascontiguousarray(packed)
+    tb = tbits_of(packed)
+    if n_blocks is None:
+        n_blocks = _blocks_of(packed, packed_len(tb, width))
+    refs, scalar = _ref_args(reference, n_blocks, packed.dtype)
+    bounds = np.array([lo, hi], dtype=packed.dtype)
+    if out is None:
+        out = np.empty(n_blocks * 128, dtype=np.uint8)
+    _run(tb, OP_UNFOR_FILTER, width, n_blocks, packed, out, base=bounds, refs=refs, ref_scalar=scalar, threads=threads)
     return out
 
 

@@ -313,7 +313,25 @@ enum Op : int {
     OP_UNDELTA_PACK = 6,
     OP_TRANSPOSE = 7,
     OP_UNTRANSPOSE = 8,
+    OP_UNFOR_FILTER = 9,  // not a reference function: unfor_pack + the caller-side predicate loop (README.md:40-41)
 };
+
+// What a user of the reference writes for a range scan (README.md:40-41: "unpack all values and then access the
+// desired one"): FoR::unfor_pack (src/ffor.rs:38-50) into a cache-resident 1024-value buffer, then one pass over
+// it.  bit i of the 128-byte block bitmap = lo <= value[i] <= hi (little-endian bit order).  The baseline the fused
+// GPU scan kernels are timed against; also their test oracle's cross-check.
+template <class T>
+inline void filter_block(const T* values, T lo, T hi, uint8_t* bitmap) {
+    const T span = T(hi - lo);
+    const bool empty = hi < lo;
+    alignas(64) uint8_t pass[1024];
+    for (int i = 0; i < 1024; ++i) pass[i] = uint8_t(T(values[i] - lo) <= span);  // vectorises: sub, cmp, narrow
+    for (int k = 0; k < 128; ++k) {
+        uint64_t x;
+        __builtin_memcpy(&x, pass + 8 * k, 8);
+        bitmap[k] = empty ? uint8_t(0) : uint8_t((x * 0x0102040810204080ull) >> 56);  // 8 bool bytes -> 8 bits
+    }
+}
 
 // `refs`: per-block reference array (may be null → `ref_scalar`); `base`: n_blocks × LANES.
 template <class T>
@@ -334,6 +352,12 @@ void run_blocks(int op, unsigned width, size_t b0, size_t b1, const T* in, T* ou
             case OP_UNDELTA_PACK: t.undelta_pack[width](in + b * pw, base + b * L, out + b * 1024); break;
             case OP_TRANSPOSE: transpose_block<T>(in + b * 1024, out + b * 1024); break;
             case OP_UNTRANSPOSE: untranspose_block<T>(in + b * 1024, out + b * 1024); break;
+            case OP_UNFOR_FILTER: {  // base = {lo, hi}; out = bitmap bytes (128 per block)
+                alignas(64) T tmp[1024];
+                t.unfor_pack[width](in + b * pw, refs ? refs[b] : ref_scalar, tmp);
+                filter_block<T>(tmp, base[0], base[1], reinterpret_cast<uint8_t*>(out) + b * 128);
+                break;
+            }
             default: break;
         }
     }

@@ -85,6 +85,24 @@ int main() {
         BitPacking<uint16_t>::unpack<W>(packed, unpacked);
         for (std::size_t i = 0; i < 1024; ++i) EXPECT(uint16_t((values[i] - 10) & ((1 << W) - 1)) == unpacked[i]);
     }
+    {   // fused scan == unfor_pack + the caller-side predicate loop (README.md:40-41), u16 W=15 ref=10 (test_ffor's data)
+        constexpr std::size_t W = 15;
+        std::array<uint16_t, 1024> values{}, decoded{};
+        for (std::size_t i = 0; i < 1024; ++i) values[i] = uint16_t(10 + i * 7 % (1 << W));
+        Packed<uint16_t, W> packed{};
+        FoR<uint16_t>::for_pack<W>(values, 10, packed);
+        FoR<uint16_t>::unfor_pack<W>(packed, 10, decoded);
+        EXPECT(decoded == values);
+        Scan<uint16_t>::Bitmap bitmap{};
+        const uint32_t count = Scan<uint16_t>::filter_range<W>(packed, 10, 100, 2000, bitmap);
+        uint32_t want = 0;
+        for (std::size_t i = 0; i < 1024; ++i) {
+            const bool sel = decoded[i] >= 100 && decoded[i] <= 2000;
+            want += sel;
+            EXPECT(bool((bitmap[i / 8] >> (i % 8)) & 1) == sel);
+        }
+        EXPECT(count == want);
+    }
     {   // index >= 1024 panics (src/bitpacking.rs:152)
         Packed<uint16_t, 3> packed{};
         bool threw = false;
