@@ -282,6 +282,26 @@ class FoR:
         _call("fl_block_minmax", i.tbits, dev, n, i.ptr, lo.ptr, hi.ptr)
 
     @staticmethod
+    def for_pack_auto(width: int, input, references, output, spans=None) -> None:
+        """`for_pack::<W>` (src/ffor.rs:24-36) with reference = each block's own minimum, found in the same pass
+        (CUDA tensors).  `references` (one per block) receives the minima; `spans` (optional) max - min per block:
+        block b round-trips losslessly iff spans[b] < 2**width."""
+        i, r, o = _Arg(input, "input"), _Arg(references, "references"), _Arg(output, "output")
+        if not _same_space(i, r, o):
+            raise FastLanesError(_lib.FL_ERR_NULL, "for_pack_auto takes CUDA tensors")
+        _check_width(width, i.tbits)
+        n = _n_blocks_unpacked(i, "Input")
+        _expect(r, n, "References")
+        _expect(o, n * packed_len(i.tbits, width), "Output")
+        sptr = None
+        if spans is not None:
+            s = _Arg(spans, "spans")
+            _same_space(i, s)
+            _expect(s, n, "Spans")
+            sptr = s.ptr
+        _lib.check(_lib.fn("fl_for_pack_auto", i.tbits)(width, n, i.ptr, r.ptr, sptr, o.ptr, _stream()))
+
+    @staticmethod
     def choose(mins, maxs, tbits: int):
         """Host helper: (reference per block, one width for the batch) = (mins, bits(max over blocks of max - min))."""
         span = (np.asarray(maxs).astype(np.uint64) - np.asarray(mins).astype(np.uint64)) & np.uint64((1 << tbits) - 1 if tbits < 64 else 0xFFFFFFFFFFFFFFFF)

@@ -259,6 +259,23 @@ fl_status host_minmax(size_t n_blocks, const T* in, T* mins, T* maxs) {
     return result;
 }
 
+// for_pack with reference = block minimum, statistics fused into the pack pass
+template <class T>
+fl_status device_for_pack_auto(unsigned width, size_t n_blocks, const T* in, T* refs_out, T* spans_out, T* packed,
+                               cudaStream_t stream) {
+    if (width > sizeof(T) * 8) return fail(FL_ERR_WIDTH, "width exceeds the bit size of the element type");
+    if (n_blocks == 0) return FL_OK;
+    if (n_blocks > (size_t(1) << 40)) return fail(FL_ERR_LEN, "n_blocks too large");
+    if (!in || !refs_out || (width && !packed)) return fail(FL_ERR_NULL, "null pointer");
+    if (!aligned16(in) || (width && !aligned16(packed))) return fail(FL_ERR_ALIGN, "device pointers must be 16-byte aligned");
+    LaunchArgs a;
+    a.in = in; a.out = packed; a.refs_out = refs_out; a.spans_out = spans_out;
+    a.n_blocks = n_blocks; a.width = width; a.stream = stream;
+    const cudaError_t e = flb::launch_pack<T>(flb::kPackForAuto, a);
+    if (e != cudaSuccess) return cuda_fail(e, "for_pack_auto launch");
+    return FL_OK;
+}
+
 // ---- fused scan (fl_scan.cuh) -------------------------------------------------------------------
 template <class T>
 fl_status device_filter(unsigned width, size_t n_blocks, const T* packed, const T* refs, T reference, T lo, T hi,
@@ -560,6 +577,10 @@ fl_status fl_shutdown(void) {
     }                                                                                                                   \
     fl_status fl_host_block_minmax_##SFX(size_t n, const T* in, T* mins, T* maxs) {                                     \
         return host_minmax<T>(n, in, mins, maxs);                                                                       \
+    }                                                                                                                   \
+    fl_status fl_for_pack_auto_##SFX(unsigned width, size_t n, const T* in, T* refs_out, T* spans_out, T* packed,       \
+                                     void* st) {                                                                       \
+        return device_for_pack_auto<T>(width, n, in, refs_out, spans_out, packed, (cudaStream_t)st);                    \
     }                                                                                                                   \
     fl_status fl_unpack_filter_##SFX(unsigned width, size_t n, const T* packed, const T* refs, T reference, T lo, T hi, \
                                      uint8_t* bitmap, uint32_t* counts, void* st) {                                    \

@@ -130,7 +130,7 @@ static cudaError_t do_pack(const LaunchArgs& a) {
     if (attr != cudaSuccess) return attr;
     pack_warp_kernel<T, W, OP, kTma><<<grid, kThreads, smem, a.stream>>>(
         static_cast<const char*>(a.in), static_cast<char*>(a.out), a.n_blocks, static_cast<const T*>(a.refs),
-        T(a.ref_scalar), static_cast<const char*>(a.base));
+        T(a.ref_scalar), static_cast<const char*>(a.base), static_cast<T*>(a.refs_out), static_cast<T*>(a.spans_out));
     return cudaGetLastError();
 }
 template <class T, int OP, int... W>
@@ -143,12 +143,19 @@ static cudaError_t pack_orig_delta(const LaunchArgs& a) {
     static constexpr auto tab = pack_table<T, POP_ORIG_DELTA>(std::make_integer_sequence<int, Lay<T>::TB + 1>{});
     return tab[a.width](a);
 }
+// for_pack with the block minimum as reference, statistics fused into the pack pass
+template <class T>
+static cudaError_t pack_for_auto(const LaunchArgs& a) {
+    static constexpr auto tab = pack_table<T, POP_FOR_AUTO>(std::make_integer_sequence<int, Lay<T>::TB + 1>{});
+    return tab[a.width](a);
+}
 template <>
 cudaError_t launch_pack<elem_t>(int op, const LaunchArgs& a) {
     using seq = std::make_integer_sequence<int, Lay<elem_t>::TB + 1>;
     static constexpr auto plain = pack_table<elem_t, POP_PLAIN>(seq{});
     static constexpr auto ffor = pack_table<elem_t, POP_FOR>(seq{});
     if (op == kPackOrigDelta) return pack_orig_delta<elem_t>(a);
+    if (op == kPackForAuto) return pack_for_auto<elem_t>(a);
     if (op == kPackPlain) return plain[a.width](a);
     if (op == kPackFor) return ffor[a.width](a);
     return cudaErrorNotSupported;

@@ -210,6 +210,40 @@ __device__ __forceinline__ Slice<T> slice_zero() {
     return o;
 }
 
+// ---- lane-wise unsigned min / max on the SWAR register (u16: one VIMNMX.U16x2) --------------------------------
+template <class T> struct MinMax;
+template <> struct MinMax<uint8_t> {
+    __device__ static uint32_t mn(uint32_t a, uint32_t b) { return __vminu4(a, b); }
+    __device__ static uint32_t mx(uint32_t a, uint32_t b) { return __vmaxu4(a, b); }
+};
+template <> struct MinMax<uint16_t> {
+    __device__ static uint32_t mn(uint32_t a, uint32_t b) { return __vminu2(a, b); }
+    __device__ static uint32_t mx(uint32_t a, uint32_t b) { return __vmaxu2(a, b); }
+};
+template <> struct MinMax<uint32_t> {
+    __device__ static uint32_t mn(uint32_t a, uint32_t b) { return min(a, b); }
+    __device__ static uint32_t mx(uint32_t a, uint32_t b) { return max(a, b); }
+};
+template <> struct MinMax<uint64_t> {
+    __device__ static uint64_t mn(uint64_t a, uint64_t b) { return min(a, b); }
+    __device__ static uint64_t mx(uint64_t a, uint64_t b) { return max(a, b); }
+};
+// reduce the SWAR lanes of one register to a single T
+template <class T>
+__device__ __forceinline__ T swar_reduce_min(typename Lay<T>::R l) {
+    using M = MinMax<T>;
+    if constexpr (sizeof(T) == 1) { uint32_t a = M::mn(l, l >> 16); a = M::mn(a, a >> 8); return T(a & 0xFF); }
+    else if constexpr (sizeof(T) == 2) return T(M::mn(l, l >> 16) & 0xFFFF);
+    else return T(l);
+}
+template <class T>
+__device__ __forceinline__ T swar_reduce_max(typename Lay<T>::R h) {
+    using M = MinMax<T>;
+    if constexpr (sizeof(T) == 1) { uint32_t b = M::mx(h, h >> 16); b = M::mx(b, b >> 8); return T(b & 0xFF); }
+    else if constexpr (sizeof(T) == 2) return T(M::mx(h, h >> 16) & 0xFFFF);
+    else return T(h);
+}
+
 // ---- unpack: bits [ROW*W, ROW*W+W) of every lane's stream  (src/macros.rs:139-170) -------------------
 // `cur` is word-row (ROW*W)/T, `nxt` word-row +1 (only read when the field straddles a word boundary).
 template <class T, int W, int ROW>

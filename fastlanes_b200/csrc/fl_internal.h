@@ -20,11 +20,13 @@ struct LaunchArgs {
     const uint64_t* offsets = nullptr;  // select: exclusive prefix of the per-block selected counts
     uint32_t* counts = nullptr;         // filter: optional per-block popcount
     uint64_t flo = 0, fhi = 0;          // filter: inclusive value range
+    void* refs_out = nullptr;           // for_pack_auto: per-block reference (= block minimum) written by the kernel
+    void* spans_out = nullptr;          // for_pack_auto: optional per-block max - min
 };
 
 // op codes of launch_unpack / launch_pack (match UnpackOp / PackOp in fl_kernels.cuh)
 enum : int { kUnpackPlain = 0, kUnpackFor = 1, kUnpackDelta = 2, kUnpackDeltaOrig = 3 };
-enum : int { kPackPlain = 0, kPackFor = 1, kPackOrigDelta = 2 };
+enum : int { kPackPlain = 0, kPackFor = 1, kPackOrigDelta = 2, kPackForAuto = 3 };
 
 // Defined once per element type in fl_codec_inst.cu (compiled with -DFLB_TBITS=8/16/32/64).
 template <class T> cudaError_t launch_unpack(int op, const LaunchArgs& a);

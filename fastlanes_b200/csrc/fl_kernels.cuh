@@ -31,7 +31,8 @@ namespace flb {
 // UOP_DELTA_ORIG: fused undelta_pack + untranspose (output in ORIGINAL value order)  — SURVEY.md §8(f) rank 1
 // POP_ORIG_DELTA: fused transpose + delta + pack   (input  in ORIGINAL value order)
 enum UnpackOp : int { UOP_PLAIN = 0, UOP_FOR = 1, UOP_DELTA = 2, UOP_DELTA_ORIG = 3 };
-enum PackOp : int { POP_PLAIN = 0, POP_FOR = 1, POP_ORIG_DELTA = 2 };
+// POP_FOR_AUTO:   for_pack with reference = the block's own minimum, computed in the same pass
+enum PackOp : int { POP_PLAIN = 0, POP_FOR = 1, POP_ORIG_DELTA = 2, POP_FOR_AUTO = 3 };
 
 #ifndef FLB_THREADS
 #define FLB_THREADS 256
@@ -297,6 +298,12 @@ __device__ __forceinline__ R shfl_reg(R v, int src) {
     else return R(__shfl_sync(0xffffffffu, v, src));
 }
 
+template <class R>
+__device__ __forceinline__ R shfl_xor_reg(R v, int mask) {
+    if constexpr (sizeof(R) == 8) return R(__shfl_xor_sync(0xffffffffu, (unsigned long long)v, mask));
+    else return R(__shfl_xor_sync(0xffffffffu, v, mask));
+}
+
 // lane-wise funnel shift LEFT by a run-time amount sh (0 <= sh < T): (hi << sh) | (lo >> (T - sh))
 template <class T>
 __device__ __forceinline__ typename Lay<T>::R lane_funnel_left_rt(typename Lay<T>::R lo, typename Lay<T>::R hi, unsigned sh,
@@ -312,17 +319,26 @@ __device__ __forceinline__ typename Lay<T>::R lane_funnel_left_rt(typename Lay<T
     }
 }
 
-// warp_decode_tile: the decode core shared by the unpack family and the fused scan kernels.  Fills the row-major
-// register tile v[i] = 16-byte slice j of row q*RPG + i of block `blk_packed` (this thread: group rank q, slice j).
+// warp_load_run / warp_extract_rows / warp_decode_tile: the decode core shared by the unpack family and the fused
+// scan kernels (this thread: group rank q, 16-byte slice j of block `blk_packed`).
+//   warp_load_run     -> a[m]: the run_words<T,W>() word-rows holding the bits of the group's RPG rows, ALIGNED: local
+//                        row i occupies bits [(i*W) % T, ...) of a[(i*W) / T], every position a compile-time constant
+//   warp_extract_rows -> v[i] = slice j of row q*RPG + i (right-aligned W-bit values)
 // TMA = true: the block's 128*W packed bytes arrive with ONE cp.async.bulk (TMA 1-D bulk copy) per warp into a
 // warp-private shared buffer, completion on a per-warp mbarrier; the word-rows are then read with LDS.128.  Every
 // packed byte crosses L2 exactly once (the direct path re-reads the word-rows that two groups share when W % 4 != 0).
 // Callers issue their independent global loads (delta bases) BEFORE this call: the mbarrier wait is a compiler
 // memory barrier, anything after it would be serialised behind the TMA round trip.
 // RESERVE: static shared memory (bytes) the calling kernel declares for itself (counts against the 48 KiB limit).
+template <class T, int W>
+__host__ __device__ constexpr int run_words() {
+    constexpr int TB = Lay<T>::TB, RPG = TB / 4;
+    return W == 0 ? 1 : (W == TB ? RPG : (RPG * W + TB - 1) / TB);
+}
+
 template <class T, int W, bool TMA, int RESERVE = 0>
-__device__ __forceinline__ void warp_decode_tile(const char* __restrict__ blk_packed, int lane, int q, int j,
-                                                 Slice<T> (&v)[WarpLay<T>::RPG]) {
+__device__ __forceinline__ void warp_load_run(const char* __restrict__ blk_packed, int lane, int q, int j,
+                                              Slice<T> (&a)[run_words<T, W>()]) {
     using R = typename Lay<T>::R;
     constexpr int TB = Lay<T>::TB;
     constexpr int RPG = WarpLay<T>::RPG;
@@ -352,13 +368,12 @@ __device__ __forceinline__ void warp_decode_tile(const char* __restrict__ blk_pa
     };
 
     if constexpr (W == 0) {
-#pragma unroll
-        for (int i = 0; i < RPG; ++i) v[i] = slice_zero<T>();
+        a[0] = slice_zero<T>();
     } else if constexpr (W == TB) {
         // macros.rs:126-132: row r is word-row r
         seq_rows<RPG>([&](auto ic) {
             constexpr int i = decltype(ic)::value;
-            v[i] = load_word_row(unsigned(q * RPG + i));
+            a[i] = load_word_row(unsigned(q * RPG + i));
         });
     } else {
         constexpr bool ALIGNED = (W % 4) == 0;              // then q*RPG*W is a multiple of T for every q
@@ -372,7 +387,6 @@ __device__ __forceinline__ void warp_decode_tile(const char* __restrict__ blk_pa
             const unsigned k = (k0 + m < unsigned(W)) ? k0 + m : unsigned(W - 1);  // clamp: never read past the block
             w[m] = load_word_row(k);
         });
-        Slice<T> a[NA];
         if constexpr (ALIGNED) {
 #pragma unroll
             for (int m = 0; m < NA; ++m) a[m] = w[m];
@@ -386,6 +400,21 @@ __device__ __forceinline__ void warp_decode_tile(const char* __restrict__ blk_pa
                 for (int r = 0; r < NR; ++r) a[m].r[r] = lane_funnel_rt<T>(w[m].r[r], w[m + 1].r[r], sh0, mlow);
             });
         }
+    }
+}
+
+template <class T, int W>
+__device__ __forceinline__ void warp_extract_rows(const Slice<T> (&a)[run_words<T, W>()], Slice<T> (&v)[WarpLay<T>::RPG]) {
+    constexpr int TB = Lay<T>::TB;
+    constexpr int RPG = WarpLay<T>::RPG;
+    if constexpr (W == 0) {
+#pragma unroll
+        for (int i = 0; i < RPG; ++i) v[i] = slice_zero<T>();
+    } else if constexpr (W == TB) {
+#pragma unroll
+        for (int i = 0; i < RPG; ++i) v[i] = a[i];
+    } else {
+        constexpr int NA = run_words<T, W>();
         seq_rows<RPG>([&](auto ic) {
             constexpr int i = decltype(ic)::value;
             constexpr int idx = (i * W) / TB;
@@ -393,6 +422,14 @@ __device__ __forceinline__ void warp_decode_tile(const char* __restrict__ blk_pa
             v[i] = extract_row<T, W, i>(a[idx], a[nxt]);
         });
     }
+}
+
+template <class T, int W, bool TMA, int RESERVE = 0>
+__device__ __forceinline__ void warp_decode_tile(const char* __restrict__ blk_packed, int lane, int q, int j,
+                                                 Slice<T> (&v)[WarpLay<T>::RPG]) {
+    Slice<T> a[run_words<T, W>()];
+    warp_load_run<T, W, TMA, RESERVE>(blk_packed, lane, q, j, a);
+    warp_extract_rows<T, W>(a, v);
 }
 
 template <class T, int W, int OP, bool TMA = false>
@@ -483,7 +520,8 @@ unpack_warp_kernel(const char* __restrict__ packed, char* __restrict__ out, size
 template <class T, int W, int OP, bool TMA = false>
 __global__ void __launch_bounds__(kThreads)
 pack_warp_kernel(const char* __restrict__ in, char* __restrict__ packed, size_t n_blocks,
-                 const T* __restrict__ refs, T ref_scalar, const char* __restrict__ base) {
+                 const T* __restrict__ refs, T ref_scalar, const char* __restrict__ base,
+                 T* __restrict__ refs_out = nullptr, T* __restrict__ spans_out = nullptr) {
     using R = typename Lay<T>::R;
     using WL = WarpLay<T>;
     constexpr int TB = Lay<T>::TB;
@@ -491,7 +529,7 @@ pack_warp_kernel(const char* __restrict__ in, char* __restrict__ packed, size_t 
     constexpr int NR = Lay<T>::NR;
     const size_t blk = (size_t(blockIdx.x) * kThreads + threadIdx.x) >> 5;
     if (blk >= n_blocks) return;  // warp-uniform
-    if constexpr (W == 0) return;  // macros.rs:52
+    if constexpr (W == 0 && OP != POP_FOR_AUTO) return;  // macros.rs:52 (FOR_AUTO still reports the statistics)
     const int lane = threadIdx.x & 31;
     const int g = lane >> 3, j = lane & 7;
     const int q = WL::rank_of_group(g);
@@ -553,7 +591,33 @@ pack_warp_kernel(const char* __restrict__ in, char* __restrict__ packed, size_t 
 #pragma unroll
         for (int i = 0; i < RPG; ++i) src[i] = slice_sub<T>(src[i], ref);
     }
-    if constexpr (W == TB) {
+    if constexpr (OP == POP_FOR_AUTO) {
+        // The statistics pass a caller runs before FoR::for_pack (which takes `reference` as a given, ffor.rs:5-10),
+        // fused: the warp already holds the whole block, so min / max are a SWAR reduction over the register tile plus
+        // a 5-step butterfly; reference = min, spans_out = max - min (the caller checks it fits W bits).
+        using M = MinMax<T>;
+        R lo = src[0].r[0], hi = lo;
+#pragma unroll
+        for (int i = 0; i < RPG; ++i)
+#pragma unroll
+            for (int r = 0; r < NR; ++r) { lo = M::mn(lo, src[i].r[r]); hi = M::mx(hi, src[i].r[r]); }
+#pragma unroll
+        for (int d = 16; d >= 1; d >>= 1) {
+            lo = M::mn(lo, shfl_xor_reg<R>(lo, d));
+            hi = M::mx(hi, shfl_xor_reg<R>(hi, d));
+        }
+        const T mn = swar_reduce_min<T>(lo), mx = swar_reduce_max<T>(hi);
+        if (lane == 0) {
+            refs_out[blk] = mn;
+            if (spans_out != nullptr) spans_out[blk] = T(mx - mn);
+        }
+        const Slice<T> ref = slice_splat<T>(mn);
+#pragma unroll
+        for (int i = 0; i < RPG; ++i) src[i] = slice_sub<T>(src[i], ref);  // ffor.rs:33
+    }
+    if constexpr (W == 0) {
+        return;  // macros.rs:52: nothing to store
+    } else if constexpr (W == TB) {
         // macros.rs:54-59: verbatim, word-row = row
         seq_rows<RPG>([&](auto ic) {
             constexpr int i = decltype(ic)::value;

@@ -144,24 +144,6 @@ cudaError_t launch_transpose(bool undo, const LaunchArgs& a) {
 // One warp = one block, linear 512-bytes-per-instruction reads, SWAR lane-wise min/max (u16: VIMNMX.U16x2),
 // then a butterfly over the warp.  Read-only: 128*T bytes per block.
 // ---------------------------------------------------------------------------------------------------
-template <class T> struct MinMax;
-template <> struct MinMax<uint8_t> {
-    __device__ static uint32_t mn(uint32_t a, uint32_t b) { return __vminu4(a, b); }
-    __device__ static uint32_t mx(uint32_t a, uint32_t b) { return __vmaxu4(a, b); }
-};
-template <> struct MinMax<uint16_t> {
-    __device__ static uint32_t mn(uint32_t a, uint32_t b) { return __vminu2(a, b); }
-    __device__ static uint32_t mx(uint32_t a, uint32_t b) { return __vmaxu2(a, b); }
-};
-template <> struct MinMax<uint32_t> {
-    __device__ static uint32_t mn(uint32_t a, uint32_t b) { return min(a, b); }
-    __device__ static uint32_t mx(uint32_t a, uint32_t b) { return max(a, b); }
-};
-template <> struct MinMax<uint64_t> {
-    __device__ static uint64_t mn(uint64_t a, uint64_t b) { return min(a, b); }
-    __device__ static uint64_t mx(uint64_t a, uint64_t b) { return max(a, b); }
-};
-
 // G threads cooperate on one block (u8: 8, u16: 16, u32/u64: 32) so that every thread reduces >= 8 chunks
 // in registers before the log2(G)-step butterfly; a warp covers 32/G consecutive blocks.
 template <class T>
@@ -199,16 +181,7 @@ block_minmax_kernel(const char* __restrict__ in, T* __restrict__ mins, T* __rest
         l = M::mn(l, ol); h = M::mx(h, oh);
     }
     if (active && t == 0) {
-        T tl, th;
-        if constexpr (sizeof(T) == 1) {
-            uint32_t a = M::mn(l, l >> 16); a = M::mn(a, a >> 8); tl = T(a & 0xFF);
-            uint32_t b = M::mx(h, h >> 16); b = M::mx(b, b >> 8); th = T(b & 0xFF);
-        } else if constexpr (sizeof(T) == 2) {
-            tl = T(M::mn(l, l >> 16) & 0xFFFF); th = T(M::mx(h, h >> 16) & 0xFFFF);
-        } else {
-            tl = T(l); th = T(h);
-        }
-        mins[blk] = tl; maxs[blk] = th;
+        mins[blk] = swar_reduce_min<T>(l); maxs[blk] = swar_reduce_max<T>(h);
     }
 }
 

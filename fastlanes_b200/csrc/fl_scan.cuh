@@ -42,6 +42,30 @@ __device__ __forceinline__ void slice_range_bits(uint32_t& acc, const Slice<T>& 
     }
 }
 
+// The values of a block are v + ref with 0 <= v <= maxv = 2^W - 1.  The predicate (v - c) mod 2^T <= span (c = lo - ref)
+// selects the cyclic interval [c, c + span]; intersected with [0, maxv] that is one interval [a, b], or everything
+// but one interval (invert = ~0), with 0 <= a <= b <= maxv.  Uniform per block: ~15 scalar instructions.
+template <class R>
+struct FieldRange {
+    R a, b;
+    uint32_t invert;  // 0: pass = a <= v <= b;  ~0: pass = !(a <= v <= b)
+};
+template <class R>
+__device__ __forceinline__ FieldRange<R> range_in_field(R c, R span, bool empty, R maxv) {
+    FieldRange<R> f{R(0), maxv, 0u};  // everything passes
+    const R e = R(c + span);
+    if (empty) {
+        f.invert = ~0u;  // nothing passes
+    } else if (e >= c) {  // the cyclic interval does not wrap
+        if (c > maxv) f.invert = ~0u;
+        else { f.a = c; f.b = e < maxv ? e : maxv; }
+    } else if (e < maxv) {  // wraps: [c, 2^T) u [0, e]; e >= maxv covers every field value
+        if (c > maxv) { f.b = e; }                                          // only [0, e] reaches the field
+        else if (R(e + 1) != c) { f.a = R(e + 1); f.b = R(c - 1); f.invert = ~0u; }  // fails exactly on (e, c)
+    }
+    return f;
+}
+
 // u32 / u64 (one lane per register): acc = 2*acc + (t > span) as a carry chain.  t > span  <=>  t + ~span carries out
 // of the register, so ADD.CC sets the carry flag to "fail" and ADDC shifts it into acc: two instructions per value,
 // no predicate / select / shift-or.  (ADD, not SUB: the carry of an addition is unambiguous, whereas after sub.cc the
@@ -68,30 +92,52 @@ filter_warp_kernel(const char* __restrict__ packed, unsigned char* __restrict__ 
     const int g = lane >> 3, j = lane & 7;
     const int q = WL::rank_of_group(g);
     const T ref = refs ? refs[blk] : ref_scalar;  // issued before the decode's TMA wait
-    Slice<T> v[RPG];
-    warp_decode_tile<T, W, TMA, (kThreads / 32) * 128>(packed + blk * (size_t(128) * W), lane, q, j, v);
+    Slice<T> a[run_words<T, W>()];
+    warp_load_run<T, W, TMA, (kThreads / 32) * 128>(packed + blk * (size_t(128) * W), lane, q, j, a);
 
-    // value = v + ref (ffor.rs:47, wrapping).  lo <= value <= hi  <=>  (v - (lo - ref)) mod 2^T <= hi - lo
-    const Slice<T> cs = slice_splat<T>(T(lo - ref)), ss = slice_splat<T>(T(hi - lo));
-    const R c = cs.r[0], span = ss.r[0];
-    R spanH = span;
-    if constexpr (sizeof(T) <= 2) spanH = span | rep_value<T>(T(T(1) << (TB - 1)));
+    // value = v + ref (ffor.rs:47, wrapping).  lo <= value <= hi  <=>  (v - c) mod 2^T <= span, c = lo - ref, span = hi - lo
     uint32_t x = 0;
-    if constexpr (sizeof(T) >= 4) {
+    if constexpr (sizeof(T) >= 4 && W > 0) {
+        // One lane per register: compare the W-bit field IN PLACE, without extracting it.  Because 0 <= v < 2^W the
+        // cyclic interval [c, c + span] restricted to [0, 2^W) is a plain interval [A, B] or the complement of one
+        // (range_in_field), so with k = T - W and the field moved to the TOP of the register (one shift-add, or one
+        // funnel shift when it straddles two words; the low k bits are garbage g < 2^k):
+        //     X - (A << k)  <=  ((B - A) << k) | (2^k - 1)      <=>      A <= v <= B
+        // -> per value: LEA/IMAD (align and subtract), ADD.CC (compare as a carry), ADDC (shift the bit in).
+        const FieldRange<R> fr = range_in_field<R>(R(T(lo - ref)), R(T(hi - lo)), hi < lo, rep_mask<T>(W));
+        constexpr int k = TB - W;
+        const R neg_a = R(0) - R(fr.a << k);
+        const R not_bound = ~R(R(R(fr.b - fr.a) << k) | R((R(1) << k) - 1));
         // values in DESCENDING bit position (row RPG-1 first): the last one shifted in lands at bit 0
-        const R not_span = ~span;
-#pragma unroll
-        for (int i = RPG - 1; i >= 0; --i)
-#pragma unroll
-            for (int r = Lay<T>::NR - 1; r >= 0; --r) shift_in_fail(x, R(v[i].r[r] - c), not_span);
-        x = ~x;  // fail bits -> pass bits  (RPG * NR == 32 values: every bit of x is one value)
-    } else {
         seq_rows<RPG>([&](auto ic) {
-            constexpr int i = decltype(ic)::value;
-            slice_range_bits<T, i * BPT>(x, v[i], c, span, spanH);
+            constexpr int i = RPG - 1 - decltype(ic)::value;
+            constexpr int idx = (i * W) / TB;
+            constexpr int sh = (i * W) % TB;
+#pragma unroll
+            for (int r = Lay<T>::NR - 1; r >= 0; --r) {
+                R top;
+                if constexpr (sh + W <= TB) top = R(a[idx].r[r] << (TB - sh - W));
+                else top = R(a[idx].r[r] >> (sh + W - TB)) | R(a[idx + 1].r[r] << (2 * TB - sh - W));  // funnel shift
+                shift_in_fail(x, R(top + neg_a), not_bound);
+            }
         });
+        x = ~x ^ fr.invert;  // fail bits -> pass bits (RPG * NR == 32 values: every bit of x is one value)
+    } else {
+        Slice<T> v[RPG];
+        warp_extract_rows<T, W>(a, v);
+        const Slice<T> cs = slice_splat<T>(T(lo - ref)), ss = slice_splat<T>(T(hi - lo));
+        const R c = cs.r[0], span = ss.r[0];
+        if constexpr (sizeof(T) >= 4) {  // W == 0: every value is 0
+            x = (R(R(0) - c) <= span) ? 0xffffffffu : 0u;
+        } else {
+            const R spanH = span | rep_value<T>(T(T(1) << (TB - 1)));
+            seq_rows<RPG>([&](auto ic) {
+                constexpr int i = decltype(ic)::value;
+                slice_range_bits<T, i * BPT>(x, v[i], c, span, spanH);
+            });
+        }
+        if (hi < lo) x = 0;  // empty range
     }
-    if (hi < lo) x = 0;  // empty range
 
     __shared__ __align__(16) unsigned char scan_tile[kThreads / 32][128];
     unsigned char* tile = scan_tile[threadIdx.x >> 5];

@@ -125,6 +125,13 @@ FL_API fl_status fl_shutdown(void);
      * n_blocks elements each. */                                                                                   \
     FL_API fl_status fl_block_minmax_##SFX(size_t n_blocks, const T* in, T* mins, T* maxs, void* stream);                  \
     FL_API fl_status fl_host_block_minmax_##SFX(size_t n_blocks, const T* in, T* mins, T* maxs);                           \
+    /* FUSED statistics + FoR::for_pack (src/ffor.rs:24-36): reference = the block's own minimum, found in the same   \
+     * pass that packs (the warp holds the whole block).  refs_out: n_blocks references (feed them to                 \
+     * fl_unfor_pack_refs); spans_out (nullable): n_blocks values max - min — the block is lossless iff                \
+     * spans_out[b] < 2^width (for_pack truncates to `width` bits like the reference, src/macros.rs:73).               \
+     * Device pointers only. */                                                                                        \
+    FL_API fl_status fl_for_pack_auto_##SFX(unsigned width, size_t n_blocks, const T* in, T* refs_out, T* spans_out,       \
+                                     T* packed, void* stream);                                                      \
     /* FUSED scan (not a trait method of the reference — README.md:40-41 tells callers to     \
      * unpack the whole block and loop over it): decode in registers, apply a range predicate, never materialise the \
      * block.  value[i] = unfor_pack(packed, reference)[i] (src/ffor.rs:38-50; reference 0 = plain unpack,           \

@@ -156,3 +156,32 @@ def test_scan_errors(fl):
         fl.Scan.filter_range(8, p[: 32 * 8], 0, 0, 1, b[:100])
     # empty batch is a no-op
     fl.Scan.filter_range(8, p[:0], 0, 0, 1, b[:0])
+
+
+@pytest.mark.parametrize("tb", [8, 16, 32, 64])
+def test_for_pack_auto_every_width(fl, oracle, tb):
+    """Fused statistics + for_pack: refs == per-block minima, spans == max - min, packed ==
+    oracle for_pack with those references (src/ffor.rs:24-36); blocks whose span fits W bits round-trip exactly."""
+    rng = np.random.default_rng(1200 + tb)
+    n = N_BLOCKS
+    for w in range(tb + 1):
+        # per-block windows [base, base + 2^w') with w' = w (lossless) or wider (truncating), incl. wrap-free extremes
+        base = rng.integers(0, 1 << (tb - 1), size=n, dtype=np.uint64)
+        wide = rng.random(n) < 0.3
+        width_of_block = np.where(wide, min(tb, w + 3), w)
+        span_cap = np.array([(1 << int(x)) - 1 for x in width_of_block], dtype=np.uint64)
+        vals = (base[:, None] + (rng.integers(0, 1 << 62, size=(n, 1024), dtype=np.uint64) & span_cap[:, None])) & np.uint64(mask(tb))
+        values = vals.astype(DT[tb]).reshape(-1)
+        refs = dev_empty(n, tb)
+        spans = dev_empty(n, tb)
+        packed = dev_empty(n * 1024 * w // tb, tb)
+        fl.FoR.for_pack_auto(w, to_dev(values), refs, packed, spans)
+        v2 = values.reshape(n, 1024)
+        assert np.array_equal(to_host(refs, tb), v2.min(1)), (tb, w, "refs")
+        assert np.array_equal(to_host(spans, tb), v2.max(1) - v2.min(1)), (tb, w, "spans")
+        assert np.array_equal(to_host(packed, tb), oracle.for_pack(values, v2.min(1), w)), (tb, w, "packed")
+        out = dev_empty(n * 1024, tb)
+        fl.FoR.unfor_pack(w, packed, refs, out)
+        fits = (v2.max(1) - v2.min(1)).astype(np.uint64) <= np.uint64(mask(w))
+        got = to_host(out, tb).reshape(n, 1024)
+        assert np.array_equal(got[fits], v2[fits]), (tb, w, "round trip of the lossless blocks")
