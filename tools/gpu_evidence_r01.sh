@@ -1,5 +1,5 @@
 #!/bin/bash
-# round 1, session 2, call 4: evidence refresh with the session-2 library: tests, both bench arms, launch list,
+# round-1 evidence pass (final library): tests, both bench arms, launch list,
 # ncu --set full of the headline kernel (W=16) and the filter kernel (W=8), full op table
 mkdir -p gpurun_out; rm -f gpurun_out/*.ncu-rep
 timeout 900 python -m pytest tests -q -m gpu > gpurun_out/pytest_gpu.log 2>&1; echo "pytest exit $?" | tee -a gpurun_out/pytest_gpu.log; tail -3 gpurun_out/pytest_gpu.log

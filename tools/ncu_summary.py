@@ -38,32 +38,36 @@ def raw_summary(path):
 
 
 def main():
+    """python tools/ncu_summary.py [round] — reads gpurun_out/ncu_raw_*.csv + gpurun_out/launches_s2.csv (what
+    tools/gpu_evidence_r01.sh leaves there) and writes profiles/ncu_s2_<round>.md, traffic_<round>.json, launches_<round>.md."""
     os.makedirs(DST, exist_ok=True)
-    lines = [f"# ncu --set full summaries, round {RND} (kernel: flb::unpack_warp_kernel<uint32_t, W, UOP_PLAIN, TMA>, 2^20 blocks)\n",
-             "Captured with `ncu --set full --clock-control none --import-source on` on build/kbench/kb_u32 (one launch after 3 warm-ups).",
+    lines = [f"# ncu --set full summaries, round {RND} (final library, launched through the C ABI by tools/ncu_one.py, 2^20 blocks)\n",
+             "`ncu --set full --clock-control none --import-source on -k regex:<kernel> -s 2 -c 1 python tools/ncu_one.py <op> 32 <W>`.",
              "Durations under ncu are serialised / replayed: use them for traffic and shares, not as bench values.\n"]
-    traffic = {}
-    for w in (1, 16, 32):
-        p = os.path.join(SRC, f"ncu_raw_unpack_u32_w{w}.csv")
+    tp = os.path.join(DST, f"traffic_{RND}.json")
+    traffic = json.load(open(tp)) if os.path.exists(tp) else {}
+    captures = [(f"unpack u32 W={w} (headline kernel)", f"ncu_raw_unpack_u32_w{w}.csv", 128 * (w + 32) << 20, f"w{w}") for w in (1, 16, 32)]
+    captures.append(("unpack_filter u32 W=8 (fused scan, lo<=v<=hi -> bitmap + counts)", "ncu_raw_filter_u32_w8.csv", (128 * 8 + 128 + 4) << 20, "filter_w8"))
+    for title, fname, alg, label in captures:
+        p = os.path.join(SRC, fname)
         if not os.path.exists(p):
             continue
         d = raw_summary(p)
-        lines.append(f"## W = {w}\n")
-        lines.append(f"kernel: `{d['Kernel Name'][0][:110]}`\n")
+        lines.append(f"## {title}\n")
+        lines.append(f"kernel: `{d['Kernel Name'][0][:140]}`\n")
         lines.append("| metric | value | unit |\n|---|---|---|")
         for k in WANT:
             if k in d:
                 lines.append(f"| {k} | {d[k][0]} | {d[k][1]} |")
         rd = to_bytes(*d["dram__bytes_read.sum"]); wr = to_bytes(*d["dram__bytes_write.sum"])
-        alg = 128 * (w + 32) * (1 << 20)
         lines.append(f"\nDRAM traffic = {rd + wr:.4g} B (read {rd:.4g} + write {wr:.4g}); algorithmic = {alg:.4g} B; ratio {((rd + wr) / alg):.3f}\n")
-        traffic[f"dram_bytes_per_launch_w{w}"] = rd + wr
-        traffic[f"algorithmic_bytes_per_launch_w{w}"] = alg
-    open(os.path.join(DST, f"ncu_unpack_u32_{RND}.md"), "w").write("\n".join(lines) + "\n")
-    json.dump(traffic, open(os.path.join(DST, f"traffic_{RND}.json"), "w"), indent=1)
+        traffic[f"dram_bytes_per_launch_{label}"] = rd + wr
+        traffic[f"algorithmic_bytes_per_launch_{label}"] = alg
+    open(os.path.join(DST, f"ncu_s2_{RND}.md"), "w").write("\n".join(lines) + "\n")
+    json.dump(traffic, open(tp, "w"), indent=1)
 
     # launch list: share of the step per kernel
-    lp = os.path.join(SRC, f"launches_{RND}.csv")
+    lp = os.path.join(SRC, "launches_s2.csv")
     if os.path.exists(lp):
         rows = [r for r in csv.reader(open(lp)) if len(r) > 10]
         hdr = rows[0]
@@ -71,20 +75,18 @@ def main():
         tot = defaultdict(float); cnt = defaultdict(int)
         for r in rows[1:]:
             name = r[ki]
-            short = "flb::unpack_warp_kernel<u32,W,PLAIN>" if "unpack_warp_kernel" in name else name.split("(")[0][:70]
+            short = "flb::unpack_warp_kernel<u32,W,PLAIN,TMA>" if "unpack_warp_kernel" in name else name.split("(")[0][:70]
             v = float(r[vi].replace(",", "")) * {"ns": 1e-3, "us": 1, "ms": 1e3, "s": 1e6}.get(r[ui], 1)
             tot[short] += v; cnt[short] += 1
         total = sum(tot.values())
-        out = [f"# Launch list of `python bench.py --steps 2 --warmup 3 --e2e-steps 0 --no-cpu` under ncu (round {RND})\n",
+        out = [f"# Launch list of `python bench.py --steps 2 --warmup 3 --e2e-steps 0 --no-cpu` under ncu (round {RND}, final library)\n",
                "`ncu --metrics gpu__time_duration.sum --clock-control none` — cold-cache, serialised: SHARES only.\n",
                "| kernel | launches | total us | share |\n|---|---|---|---|"]
         for k in sorted(tot, key=tot.get, reverse=True):
             out.append(f"| `{k}` | {cnt[k]} | {tot[k]:.1f} | {tot[k] / total:.3%} |")
-        out.append("\nThe only non-library kernel in the timed region of bench.py is unpack_warp_kernel (32 launches per step);"
+        out.append("\nThe only library kernel in the timed region of bench.py is unpack_warp_kernel (32 launches per step);"
                    " the torch `random_` kernels generate the synthetic packed input before timing starts.")
         open(os.path.join(DST, f"launches_{RND}.md"), "w").write("\n".join(out) + "\n")
-    print(open(os.path.join(DST, f"ncu_unpack_u32_{RND}.md")).read()[:3000])
-    if os.path.exists(lp):
         print(open(os.path.join(DST, f"launches_{RND}.md")).read())
 
 
