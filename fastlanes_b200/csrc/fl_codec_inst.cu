@@ -164,11 +164,15 @@ cudaError_t launch_pack<elem_t>(int op, const LaunchArgs& a) {
 // fused decode + predicate kernels (fl_scan.cuh)
 template <class T, int W>
 static cudaError_t do_filter(const LaunchArgs& a) {
-    const unsigned grid = unsigned((a.n_blocks * 32 + kThreads - 1) / kThreads);
+    // blocks per warp: 4 amortises the per-warp set-up while the filter is issue-bound (u32 W=8: 285 -> 208 us); from
+    // W ~ 3T/4 it is HBM-bound and one block per warp keeps more loads in flight (profiles/opbench_scan_r01.txt)
+    constexpr int kNB = (4 * W >= 3 * Lay<T>::TB) ? 1 : 4;
+    const size_t warps = (a.n_blocks + kNB - 1) / kNB;
+    const unsigned grid = unsigned((warps * 32 + kThreads - 1) / kThreads);
     // Direct 128-bit loads, not the TMA bulk load: the filter reads little per block and is ALU-bound below W ~ 3T/4,
     // where the mbarrier round trip costs 10-15 % (u32 W=8: 300 vs 346 us; equal at W >= 29 —
     // profiles/opbench_filter_tma_r01.txt).
-    filter_warp_kernel<T, W, false><<<grid, kThreads, 0, a.stream>>>(
+    filter_warp_kernel<T, W, false, kNB><<<grid, kThreads, 0, a.stream>>>(
         static_cast<const char*>(a.in), static_cast<unsigned char*>(a.out), a.counts, a.n_blocks,
         static_cast<const T*>(a.refs), T(a.ref_scalar), T(a.flo), T(a.fhi));
     return cudaGetLastError();

@@ -77,7 +77,35 @@ __device__ __forceinline__ void shift_in_fail(uint32_t& acc, uint64_t t, uint64_
     asm("{\n .reg .u64 d;\n add.cc.u64 d, %1, %2;\n addc.u32 %0, %0, %0;\n}" : "+r"(acc) : "l"(t), "l"(not_span));
 }
 
-template <class T, int W, bool TMA>
+// Block-invariant part of the predicate for one FoR reference (per block only when `refs` is given).
+template <class T, int W>
+struct FilterPred {
+    using R = typename Lay<T>::R;
+    static constexpr bool IN_PLACE = sizeof(T) >= 4 && W > 0;
+    R p0, p1, p2;      // IN_PLACE: neg_a, not_bound, -      else: c, span, span | H
+    uint32_t invert;   // IN_PLACE: XOR mask of the result   else: ~0 when the range is empty (hi < lo)
+    __device__ __forceinline__ FilterPred(T ref, T lo, T hi) {
+        constexpr int TB = Lay<T>::TB;
+        if constexpr (IN_PLACE) {
+            const FieldRange<R> fr = range_in_field<R>(R(T(lo - ref)), R(T(hi - lo)), hi < lo, rep_mask<T>(W));
+            constexpr int k = TB - W;
+            p0 = R(0) - R(fr.a << k);
+            p1 = ~R(R(R(fr.b - fr.a) << k) | R((R(1) << k) - 1));
+            p2 = 0;
+            invert = fr.invert;
+        } else {
+            p0 = slice_splat<T>(T(lo - ref)).r[0];
+            p1 = slice_splat<T>(T(hi - lo)).r[0];
+            p2 = p1;
+            if constexpr (sizeof(T) <= 2) p2 = p1 | rep_value<T>(T(T(1) << (TB - 1)));
+            invert = (hi < lo) ? ~0u : 0u;
+        }
+    }
+};
+
+// NB consecutive blocks per warp: the per-warp set-up (thread mapping, tile address, and — with a scalar reference —
+// the whole FilterPred) is paid once per NB blocks; the filter is issue-bound below W ~ 3T/4, so this is throughput.
+template <class T, int W, bool TMA, int NB>
 __global__ void __launch_bounds__(kThreads)
 filter_warp_kernel(const char* __restrict__ packed, unsigned char* __restrict__ bitmap, uint32_t* __restrict__ counts,
                    size_t n_blocks, const T* __restrict__ refs, T ref_scalar, T lo, T hi) {
@@ -86,74 +114,78 @@ filter_warp_kernel(const char* __restrict__ packed, unsigned char* __restrict__ 
     constexpr int TB = Lay<T>::TB;
     constexpr int RPG = WL::RPG;
     constexpr int BPT = 128 / TB;  // predicate bits per thread per row
-    const size_t blk = (size_t(blockIdx.x) * kThreads + threadIdx.x) >> 5;
-    if (blk >= n_blocks) return;  // warp-uniform
+    const size_t blk0 = ((size_t(blockIdx.x) * kThreads + threadIdx.x) >> 5) * NB;
+    if (blk0 >= n_blocks) return;  // warp-uniform
     const int lane = threadIdx.x & 31;
     const int g = lane >> 3, j = lane & 7;
     const int q = WL::rank_of_group(g);
-    const T ref = refs ? refs[blk] : ref_scalar;  // issued before the decode's TMA wait
-    Slice<T> a[run_words<T, W>()];
-    warp_load_run<T, W, TMA, (kThreads / 32) * 128>(packed + blk * (size_t(128) * W), lane, q, j, a);
-
-    // value = v + ref (ffor.rs:47, wrapping).  lo <= value <= hi  <=>  (v - c) mod 2^T <= span, c = lo - ref, span = hi - lo
-    uint32_t x = 0;
-    if constexpr (sizeof(T) >= 4 && W > 0) {
-        // One lane per register: compare the W-bit field IN PLACE, without extracting it.  Because 0 <= v < 2^W the
-        // cyclic interval [c, c + span] restricted to [0, 2^W) is a plain interval [A, B] or the complement of one
-        // (range_in_field), so with k = T - W and the field moved to the TOP of the register (one shift-add, or one
-        // funnel shift when it straddles two words; the low k bits are garbage g < 2^k):
-        //     X - (A << k)  <=  ((B - A) << k) | (2^k - 1)      <=>      A <= v <= B
-        // -> per value: LEA/IMAD (align and subtract), ADD.CC (compare as a carry), ADDC (shift the bit in).
-        const FieldRange<R> fr = range_in_field<R>(R(T(lo - ref)), R(T(hi - lo)), hi < lo, rep_mask<T>(W));
-        constexpr int k = TB - W;
-        const R neg_a = R(0) - R(fr.a << k);
-        const R not_bound = ~R(R(R(fr.b - fr.a) << k) | R((R(1) << k) - 1));
-        // values in DESCENDING bit position (row RPG-1 first): the last one shifted in lands at bit 0
-        seq_rows<RPG>([&](auto ic) {
-            constexpr int i = RPG - 1 - decltype(ic)::value;
-            constexpr int idx = (i * W) / TB;
-            constexpr int sh = (i * W) % TB;
-#pragma unroll
-            for (int r = Lay<T>::NR - 1; r >= 0; --r) {
-                R top;
-                if constexpr (sh + W <= TB) top = R(a[idx].r[r] << (TB - sh - W));
-                else top = R(a[idx].r[r] >> (sh + W - TB)) | R(a[idx + 1].r[r] << (2 * TB - sh - W));  // funnel shift
-                shift_in_fail(x, R(top + neg_a), not_bound);
-            }
-        });
-        x = ~x ^ fr.invert;  // fail bits -> pass bits (RPG * NR == 32 values: every bit of x is one value)
-    } else {
-        Slice<T> v[RPG];
-        warp_extract_rows<T, W>(a, v);
-        const Slice<T> cs = slice_splat<T>(T(lo - ref)), ss = slice_splat<T>(T(hi - lo));
-        const R c = cs.r[0], span = ss.r[0];
-        if constexpr (sizeof(T) >= 4) {  // W == 0: every value is 0
-            x = (R(R(0) - c) <= span) ? 0xffffffffu : 0u;
-        } else {
-            const R spanH = span | rep_value<T>(T(T(1) << (TB - 1)));
-            seq_rows<RPG>([&](auto ic) {
-                constexpr int i = decltype(ic)::value;
-                slice_range_bits<T, i * BPT>(x, v[i], c, span, spanH);
-            });
-        }
-        if (hi < lo) x = 0;  // empty range
-    }
-
     __shared__ __align__(16) unsigned char scan_tile[kThreads / 32][128];
     unsigned char* tile = scan_tile[threadIdx.x >> 5];
-    if constexpr (sizeof(T) == 4) {
-        x = merge_pair_bpt4(x, __shfl_xor_sync(0xffffffffu, x, 1), j);
-    } else if constexpr (sizeof(T) == 8) {
-        x = merge_pair_bpt2(x, __shfl_xor_sync(0xffffffffu, x, 1), j);
-        x = merge_quad_bpt2(x, __shfl_xor_sync(0xffffffffu, x, 2), j);
-    }
-    scan_store<TB>(tile, q, j, x);
-    __syncwarp();
-    const uint32_t word = reinterpret_cast<const uint32_t*>(tile)[lane];
-    reinterpret_cast<uint32_t*>(bitmap + blk * 128)[lane] = word;  // one 128-byte line per warp
-    if (counts != nullptr) {
-        const uint32_t n = __reduce_add_sync(0xffffffffu, uint32_t(__popc(word)));
-        if (lane == 0) counts[blk] = n;
+    FilterPred<T, W> pred(ref_scalar, lo, hi);
+
+#pragma unroll 1
+    for (int nb = 0; nb < NB; ++nb) {
+        const size_t blk = blk0 + nb;
+        if (blk >= n_blocks) break;  // warp-uniform
+        if (refs != nullptr) pred = FilterPred<T, W>(refs[blk], lo, hi);
+        Slice<T> a[run_words<T, W>()];
+        warp_load_run<T, W, TMA, (kThreads / 32) * 128>(packed + blk * (size_t(128) * W), lane, q, j, a);
+
+        // value = v + ref (ffor.rs:47, wrapping).  lo <= value <= hi  <=>  (v - c) mod 2^T <= span, c = lo - ref, span = hi - lo
+        uint32_t x = 0;
+        if constexpr (FilterPred<T, W>::IN_PLACE) {
+            // One lane per register: compare the W-bit field IN PLACE, without extracting it.  Because 0 <= v < 2^W the
+            // cyclic interval [c, c + span] restricted to [0, 2^W) is a plain interval [A, B] or the complement of one
+            // (range_in_field), so with k = T - W and the field moved to the TOP of the register (one shift-add, or one
+            // funnel shift when it straddles two words; the low k bits are garbage g < 2^k):
+            //     X - (A << k)  <=  ((B - A) << k) | (2^k - 1)      <=>      A <= v <= B
+            // -> per value: LEA/IMAD (align and subtract), ADD.CC (compare as a carry), ADDC (shift the bit in).
+            const R neg_a = pred.p0, not_bound = pred.p1;
+            // values in DESCENDING bit position (row RPG-1 first): the last one shifted in lands at bit 0
+            seq_rows<RPG>([&](auto ic) {
+                constexpr int i = RPG - 1 - decltype(ic)::value;
+                constexpr int idx = (i * W) / TB;
+                constexpr int sh = (i * W) % TB;
+#pragma unroll
+                for (int r = Lay<T>::NR - 1; r >= 0; --r) {
+                    R top;
+                    if constexpr (sh + W <= TB) top = R(a[idx].r[r] << (TB - sh - W));
+                    else top = R(a[idx].r[r] >> (sh + W - TB)) | R(a[idx + 1].r[r] << (2 * TB - sh - W));  // funnel shift
+                    shift_in_fail(x, R(top + neg_a), not_bound);
+                }
+            });
+            x = ~x ^ pred.invert;  // fail bits -> pass bits (RPG * NR == 32 values: every bit of x is one value)
+        } else {
+            Slice<T> v[RPG];
+            warp_extract_rows<T, W>(a, v);
+            const R c = pred.p0, span = pred.p1;
+            if constexpr (sizeof(T) >= 4) {  // W == 0: every value is 0
+                x = (R(R(0) - c) <= span) ? 0xffffffffu : 0u;
+            } else {
+                const R spanH = pred.p2;
+                seq_rows<RPG>([&](auto ic) {
+                    constexpr int i = decltype(ic)::value;
+                    slice_range_bits<T, i * BPT>(x, v[i], c, span, spanH);
+                });
+            }
+            x &= ~pred.invert;  // empty range
+        }
+
+        if constexpr (sizeof(T) == 4) {
+            x = merge_pair_bpt4(x, __shfl_xor_sync(0xffffffffu, x, 1), j);
+        } else if constexpr (sizeof(T) == 8) {
+            x = merge_pair_bpt2(x, __shfl_xor_sync(0xffffffffu, x, 1), j);
+            x = merge_quad_bpt2(x, __shfl_xor_sync(0xffffffffu, x, 2), j);
+        }
+        scan_store<TB>(tile, q, j, x);
+        __syncwarp();
+        const uint32_t word = reinterpret_cast<const uint32_t*>(tile)[lane];
+        reinterpret_cast<uint32_t*>(bitmap + blk * 128)[lane] = word;  // one 128-byte line per warp
+        if (counts != nullptr) {
+            const uint32_t n = __reduce_add_sync(0xffffffffu, uint32_t(__popc(word)));
+            if (lane == 0) counts[blk] = n;
+        }
+        __syncwarp();  // the tile is rewritten by the next block
     }
 }
 
