@@ -595,18 +595,30 @@ pack_warp_kernel(const char* __restrict__ in, char* __restrict__ packed, size_t 
         // The statistics pass a caller runs before FoR::for_pack (which takes `reference` as a given, ffor.rs:5-10),
         // fused: the warp already holds the whole block, so min / max are a SWAR reduction over the register tile plus
         // a 5-step butterfly; reference = min, spans_out = max - min (the caller checks it fits W bits).
-        using M = MinMax<T>;
-        R lo = src[0].r[0], hi = lo;
+        using M = MinMax<typename std::conditional<sizeof(T) == 1, uint16_t, T>::type>;  // u8 reduces as 16x2 (below)
+        R lo, hi;
+        if constexpr (sizeof(T) == 1) {
+            uint32_t mn_e = 0x00FF00FFu, mn_o = 0x00FF00FFu, mx_e = 0, mx_o = 0;
 #pragma unroll
-        for (int i = 0; i < RPG; ++i)
+            for (int i = 0; i < RPG; ++i)
 #pragma unroll
-            for (int r = 0; r < NR; ++r) { lo = M::mn(lo, src[i].r[r]); hi = M::mx(hi, src[i].r[r]); }
+                for (int r = 0; r < NR; ++r) u8_minmax_acc(src[i].r[r], mn_e, mn_o, mx_e, mx_o);
+            lo = __vminu2(mn_e, mn_o); hi = __vmaxu2(mx_e, mx_o);  // two 16-bit lanes holding byte values
+        } else {
+            lo = src[0].r[0]; hi = lo;
+#pragma unroll
+            for (int i = 0; i < RPG; ++i)
+#pragma unroll
+                for (int r = 0; r < NR; ++r) { lo = M::mn(lo, src[i].r[r]); hi = M::mx(hi, src[i].r[r]); }
+        }
 #pragma unroll
         for (int d = 16; d >= 1; d >>= 1) {
             lo = M::mn(lo, shfl_xor_reg<R>(lo, d));
             hi = M::mx(hi, shfl_xor_reg<R>(hi, d));
         }
-        const T mn = swar_reduce_min<T>(lo), mx = swar_reduce_max<T>(hi);
+        T mn, mx;
+        if constexpr (sizeof(T) == 1) { mn = T(min(lo & 0xFFFFu, lo >> 16)); mx = T(max(hi & 0xFFFFu, hi >> 16)); }
+        else { mn = swar_reduce_min<T>(lo); mx = swar_reduce_max<T>(hi); }
         if (lane == 0) {
             refs_out[blk] = mn;
             if (spans_out != nullptr) spans_out[blk] = T(mx - mn);

@@ -1,4 +1,6 @@
 // fl_misc.cu — transpose / untranspose (a14) and batched unpack_single (a11/a12) kernels, all types.
+#include <cstdlib>
+
 #include "fl_device.cuh"
 #include "fl_internal.h"
 
@@ -146,30 +148,43 @@ cudaError_t launch_transpose(bool undo, const LaunchArgs& a) {
 // ---------------------------------------------------------------------------------------------------
 // G threads cooperate on one block (u8: 8, u16: 16, u32/u64: 32) so that every thread reduces >= 8 chunks
 // in registers before the log2(G)-step butterfly; a warp covers 32/G consecutive blocks.
-template <class T>
+template <class T, int G>
 __global__ void __launch_bounds__(256)
 block_minmax_kernel(const char* __restrict__ in, T* __restrict__ mins, T* __restrict__ maxs, size_t n_blocks) {
     using R = typename Lay<T>::R;
     using M = MinMax<T>;
     constexpr int TB = Lay<T>::TB;
     constexpr int NR = Lay<T>::NR;
-    constexpr int G = (sizeof(T) == 1) ? 8 : (sizeof(T) == 2 ? 16 : 32);
     constexpr int CHUNKS = (128 * TB) / 16;  // 16-byte chunks per block
     const size_t tid = size_t(blockIdx.x) * 256 + threadIdx.x;
     const size_t blk = tid / G;
     const int t = int(tid % G);
     const bool active = blk < n_blocks;  // whole groups are active or not; shuffles below stay inside a group
     const char* ib = in + (active ? blk : 0) * (size_t(128) * TB) + t * 16;
-    Slice<T> lo = load_slice<T>(ib), hi = lo;
+    R l, h;
+    if constexpr (sizeof(T) == 1) {
+        // u8: 16x2 split accumulators (u8_minmax_acc); the SWAR 8x4 intrinsics made this kernel ALU-bound at 5.1 TB/s
+        uint32_t mn_e = 0x00FF00FFu, mn_o = 0x00FF00FFu, mx_e = 0, mx_o = 0;
 #pragma unroll
-    for (int i = 1; i < CHUNKS / G; ++i) {
-        const Slice<T> v = load_slice<T>(ib + i * (G * 16));
+        for (int i = 0; i < CHUNKS / G; ++i) {
+            const Slice<T> v = load_slice<T>(ib + i * (G * 16));
 #pragma unroll
-        for (int r = 0; r < NR; ++r) { lo.r[r] = M::mn(lo.r[r], v.r[r]); hi.r[r] = M::mx(hi.r[r], v.r[r]); }
+            for (int r = 0; r < NR; ++r) u8_minmax_acc(v.r[r], mn_e, mn_o, mx_e, mx_o);
+        }
+        l = __vminu2(mn_e, mn_o);  // two 16-bit lanes, values <= 255
+        h = __vmaxu2(mx_e, mx_o);
+    } else {
+        Slice<T> lo = load_slice<T>(ib), hi = lo;
+#pragma unroll
+        for (int i = 1; i < CHUNKS / G; ++i) {
+            const Slice<T> v = load_slice<T>(ib + i * (G * 16));
+#pragma unroll
+            for (int r = 0; r < NR; ++r) { lo.r[r] = M::mn(lo.r[r], v.r[r]); hi.r[r] = M::mx(hi.r[r], v.r[r]); }
+        }
+        l = lo.r[0]; h = hi.r[0];
+#pragma unroll
+        for (int r = 1; r < NR; ++r) { l = M::mn(l, lo.r[r]); h = M::mx(h, hi.r[r]); }
     }
-    R l = lo.r[0], h = hi.r[0];
-#pragma unroll
-    for (int r = 1; r < NR; ++r) { l = M::mn(l, lo.r[r]); h = M::mx(h, hi.r[r]); }
 #pragma unroll
     for (int d = G / 2; d >= 1; d >>= 1) {
         R ol, oh;
@@ -178,19 +193,38 @@ block_minmax_kernel(const char* __restrict__ in, T* __restrict__ mins, T* __rest
         } else {
             ol = __shfl_xor_sync(0xffffffffu, l, d); oh = __shfl_xor_sync(0xffffffffu, h, d);
         }
-        l = M::mn(l, ol); h = M::mx(h, oh);
+        if constexpr (sizeof(T) == 1) { l = __vminu2(l, ol); h = __vmaxu2(h, oh); }
+        else { l = M::mn(l, ol); h = M::mx(h, oh); }
     }
     if (active && t == 0) {
-        mins[blk] = swar_reduce_min<T>(l); maxs[blk] = swar_reduce_max<T>(h);
+        if constexpr (sizeof(T) == 1) {  // l / h hold two 16-bit lanes
+            mins[blk] = T(min(l & 0xFFFFu, l >> 16)); maxs[blk] = T(max(h & 0xFFFFu, h >> 16));
+        } else {
+            mins[blk] = swar_reduce_min<T>(l); maxs[blk] = swar_reduce_max<T>(h);
+        }
     }
 }
 
 template <class T>
 cudaError_t launch_block_minmax(size_t n_blocks, const T* in, T* mins, T* maxs, cudaStream_t stream) {
     if (n_blocks == 0) return cudaSuccess;
-    constexpr int G = (sizeof(T) == 1) ? 8 : (sizeof(T) == 2 ? 16 : 32);
-    const unsigned grid = unsigned((n_blocks * G + 255) / 256);
-    block_minmax_kernel<T><<<grid, 256, 0, stream>>>(reinterpret_cast<const char*>(in), mins, maxs, n_blocks);
+    if constexpr (sizeof(T) == 1) {
+        // FLB_MINMAX_G8=8|16|32: threads per u8 block (A/B measurement; default = measured best)
+        static const int g8 = [] {
+            const char* e = std::getenv("FLB_MINMAX_G8");
+            const int v = e ? std::atoi(e) : 8;
+            return (v == 16 || v == 32) ? v : 8;
+        }();
+        const unsigned grid = unsigned((n_blocks * g8 + 255) / 256);
+        const char* p = reinterpret_cast<const char*>(in);
+        if (g8 == 16) block_minmax_kernel<T, 16><<<grid, 256, 0, stream>>>(p, mins, maxs, n_blocks);
+        else if (g8 == 32) block_minmax_kernel<T, 32><<<grid, 256, 0, stream>>>(p, mins, maxs, n_blocks);
+        else block_minmax_kernel<T, 8><<<grid, 256, 0, stream>>>(p, mins, maxs, n_blocks);
+    } else {
+        constexpr int G = (sizeof(T) == 2) ? 16 : 32;
+        const unsigned grid = unsigned((n_blocks * G + 255) / 256);
+        block_minmax_kernel<T, G><<<grid, 256, 0, stream>>>(reinterpret_cast<const char*>(in), mins, maxs, n_blocks);
+    }
     return cudaGetLastError();
 }
 
