@@ -464,6 +464,7 @@ def main():
                "d2h_bytes_per_step": len(WIDTHS) * n_blocks * 4096,
                "steps": args.e2e_steps, "ms_per_step": round(e2e_s / args.e2e_steps * 1e3, 1),
                "api": "fl_host_unpack_u32 (pinned host buffers, chunked 3-stream H2D/kernel/D2H pipeline), per rank",
+               "pinned_numa_node": _lib.lib().fl_device_numa_node(local_rank) if os.environ.get("FLB_NUMA", "1") != "0" else None,
                "timing": "host wall clock around the synchronous C-ABI calls (includes PCIe copies), max over ranks"}
         # last call's result must equal the device result of the same width
         check = torch.from_numpy(h_out.view(np.int32)[: 1 << 20]).to(dev)

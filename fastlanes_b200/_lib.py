@@ -33,7 +33,7 @@ _PER_TYPE = {
     "fl_transpose": "npps", "fl_untranspose": "npps",
     "fl_host_transpose": "npp", "fl_host_untranspose": "npp",
 }
-_GLOBAL = ["fl_version", "fl_last_error_string", "fl_status_string", "fl_device_count", "fl_init", "fl_host_configure",
+_GLOBAL = ["fl_version", "fl_last_error_string", "fl_status_string", "fl_device_count", "fl_device_numa_node", "fl_init", "fl_host_configure",
            "fl_host_alloc", "fl_host_free", "fl_host_register", "fl_host_unregister", "fl_shutdown"]
 
 
@@ -71,6 +71,8 @@ def lib() -> ctypes.CDLL:
     L.fl_status_string.argtypes = [ctypes.c_int]
     L.fl_device_count.restype = ctypes.c_int
     L.fl_init.argtypes = [ctypes.c_int]
+    L.fl_device_numa_node.restype = ctypes.c_int
+    L.fl_device_numa_node.argtypes = [ctypes.c_int]
     L.fl_host_configure.argtypes = [ctypes.c_size_t, ctypes.c_int]
     L.fl_host_alloc.argtypes = [ctypes.POINTER(ctypes.c_void_p), ctypes.c_size_t]
     L.fl_host_free.argtypes = [ctypes.c_void_p]

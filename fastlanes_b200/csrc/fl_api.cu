@@ -3,7 +3,10 @@
 // Device family: argument checks + one kernel launch on the caller's stream.
 // Host family:   chunked H2D -> kernel -> D2H pipeline over internal streams (per-device context).
 // There is no CPU compute path anywhere in this library: every value is produced by a CUDA kernel.
+#include <sched.h>
+
 #include <atomic>
+#include <cctype>
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
@@ -107,6 +110,45 @@ fl_status device_op(Op op, unsigned width, size_t n_blocks, const void* in, void
     }
     if (e != cudaSuccess) return cuda_fail(e, "kernel launch");
     return FL_OK;
+}
+
+// ---- NUMA placement of page-locked host memory ---------------------------------------------------
+// node of the PCIe device behind CUDA device `dev` (sysfs), or -1 when unknown
+int device_numa_node(int dev) {
+    char id[32] = {0};
+    if (cudaDeviceGetPCIBusId(id, int(sizeof(id)), dev) != cudaSuccess) { (void)cudaGetLastError(); return -1; }
+    for (char* c = id; *c; ++c) *c = char(std::tolower(static_cast<unsigned char>(*c)));
+    const std::string path = std::string("/sys/bus/pci/devices/") + id + "/numa_node";
+    FILE* f = std::fopen(path.c_str(), "r");
+    if (!f) return -1;
+    int node = -1;
+    if (std::fscanf(f, "%d", &node) != 1) node = -1;
+    std::fclose(f);
+    return node;
+}
+// CPUs of a NUMA node from /sys/devices/system/node/node<N>/cpulist ("0-31,64-95")
+bool node_cpuset(int node, cpu_set_t* set) {
+    if (node < 0) return false;
+    const std::string path = "/sys/devices/system/node/node" + std::to_string(node) + "/cpulist";
+    FILE* f = std::fopen(path.c_str(), "r");
+    if (!f) return false;
+    char buf[4096] = {0};
+    const bool ok = std::fgets(buf, sizeof(buf), f) != nullptr;
+    std::fclose(f);
+    if (!ok) return false;
+    CPU_ZERO(set);
+    int n = 0;
+    for (const char* p = buf; *p && *p != '\n';) {
+        char* end = nullptr;
+        const long a = std::strtol(p, &end, 10);
+        if (end == p) return false;
+        long b = a;
+        p = end;
+        if (*p == '-') { b = std::strtol(p + 1, &end, 10); if (end == p + 1) return false; p = end; }
+        for (long c = a; c <= b && c < CPU_SETSIZE; ++c) { CPU_SET(int(c), set); ++n; }
+        if (*p == ',') ++p;
+    }
+    return n > 0;
 }
 
 // ---- host path ----------------------------------------------------------------------------------
@@ -455,9 +497,26 @@ fl_status fl_host_configure(size_t chunk_blocks, int n_streams) {
     g_n_streams.store(n_streams > 0 ? (n_streams > 16 ? 16 : n_streams) : 3);
     return FL_OK;
 }
+int fl_device_numa_node(int device) { return device_numa_node(device); }
 fl_status fl_host_alloc(void** p, size_t bytes) {
     if (!p) return fail(FL_ERR_NULL, "null pointer");
-    FL_CUDA(cudaHostAlloc(p, bytes, cudaHostAllocDefault));
+    // NUMA-local staging: the pages of a page-locked allocation are placed on the node of the allocating thread, so
+    // run the allocation on a CPU of the GPU's own node (a D2H stream that crosses the socket interconnect loses
+    // bandwidth, and with one rank per GPU every rank would otherwise land on whatever node it was started on).
+    // FLB_NUMA=0 disables; any failure falls back to a plain allocation.
+    int dev = -1;
+    cpu_set_t local, saved;
+    bool bound = false;
+    const char* e = std::getenv("FLB_NUMA");
+    if (!(e && e[0] == '0') && cudaGetDevice(&dev) == cudaSuccess && node_cpuset(device_numa_node(dev), &local) &&
+        sched_getaffinity(0, sizeof(saved), &saved) == 0) {
+        cpu_set_t want;
+        CPU_AND(&want, &local, &saved);  // stay inside the CPUs this thread may use
+        if (CPU_COUNT(&want) > 0 && sched_setaffinity(0, sizeof(want), &want) == 0) bound = true;
+    }
+    const cudaError_t err = cudaHostAlloc(p, bytes, cudaHostAllocDefault);
+    if (bound) (void)sched_setaffinity(0, sizeof(saved), &saved);
+    if (err != cudaSuccess) return cuda_fail(err, "cudaHostAlloc");
     return FL_OK;
 }
 fl_status fl_host_free(void* p) {

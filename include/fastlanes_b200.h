@@ -63,7 +63,11 @@ FL_API fl_status fl_init(int device);
 /* Host-path tuning for the CURRENT device: blocks per pipelined chunk (0 = default 16384) and
  * number of internal streams (0 = default 3).  Takes effect on the next fl_host_* call. */
 FL_API fl_status fl_host_configure(size_t chunk_blocks, int n_streams);
-/* Page-locked host memory helpers (cudaHostAlloc / cudaHostRegister). */
+/* Page-locked host memory helpers (cudaHostAlloc / cudaHostRegister).  fl_host_alloc places the pages on the NUMA
+ * node of the CURRENT device (it runs the allocation on a CPU of that node; FLB_NUMA=0 disables): a D2H stream that
+ * crosses the socket interconnect is slower, and the host family is PCIe-bound.  fl_device_numa_node: that node, or
+ * -1 when the platform does not say — bind the threads that produce / consume the buffers to it as well. */
+FL_API int fl_device_numa_node(int device);
 FL_API fl_status fl_host_alloc(void** p, size_t bytes);
 FL_API fl_status fl_host_free(void* p);
 FL_API fl_status fl_host_register(void* p, size_t bytes);

@@ -22,7 +22,7 @@ def test_library_exports_every_declared_symbol():
 
     L = ctypes.CDLL(_lib.LIB_PATH)
     declared = declared_symbols()
-    assert len(declared) == 11 + 33 * 4
+    assert len(declared) == 12 + 33 * 4
     for name in sorted(declared):
         assert hasattr(L, name), f"{name} declared in include/fastlanes_b200.h but not exported"
     assert declared == set(_lib.exported_symbols())
@@ -72,3 +72,12 @@ def test_host_mirror_argument_checks_need_no_device():
     assert e.value.status == 3  # assert!(index < 1024) (bitpacking.rs:152)
     assert fl.Transpose.transpose_index(1) == 64 and fl.Transpose.transpose_index(16) == 32
     assert fl.FastLanes(32).LANES == 32 and fl.packed_len(16, 3) == 192
+
+
+def test_header_is_plain_c():
+    """The boundary is a C ABI: the header must compile as C99 with no extensions (what cgo / bindgen / cffi consume)."""
+    import subprocess
+
+    r = subprocess.run(["gcc", "-std=c99", "-Wall", "-Wextra", "-pedantic", "-Werror", "-fsyntax-only", "-x", "c",
+                        os.path.join(ROOT, "include", "fastlanes_b200.h")], capture_output=True, text=True)
+    assert r.returncode == 0, r.stderr

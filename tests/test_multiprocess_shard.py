@@ -74,3 +74,46 @@ def test_two_rank_sharded_decode_matches_single_rank(tmp_path, oracle):
     parts = [int(np.load(tmp_path / f"shard{r}.npy").astype(np.uint64).sum() & np.uint64((1 << 62) - 1)) for r in range(world)]
     assert chks[0] == chks[1] == sum(parts)
     assert (sum(parts) - expect_chk) % (1 << 62) == 0
+
+
+def _scatter_worker(rank, world, port, n_blocks, width, tmpdir):
+    import torch
+    import torch.distributed as dist
+
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port), RANK=str(rank), WORLD_SIZE=str(world))
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    try:
+        from fastlanes_b200.shard import block_shard, gather_blocks, scatter_blocks
+        from oracle import fl_oracle as oracle
+
+        per = 32 * width
+        src = None
+        if rank == 0:  # only the root holds the column
+            rng = np.random.default_rng(321)
+            src = torch.from_numpy(rng.integers(0, 1 << 31, size=n_blocks * per, dtype=np.int64).astype(np.int32))
+        mine = scatter_blocks(src, n_blocks, per, dist)
+        b0, b1 = block_shard(n_blocks, rank, world)
+        assert mine.numel() == (b1 - b0) * per
+        # decode the shard (the CPU oracle stands in for the GPU kernel), reduce it to per-block counts, gather those
+        vals = oracle.unpack(mine.numpy().view(np.uint32), width, n_blocks=b1 - b0).reshape(b1 - b0, 1024)
+        counts = torch.from_numpy((vals < (1 << (width - 1))).sum(1).astype(np.int32))
+        allc = gather_blocks(counts, n_blocks, 1, dist)
+        assert allc.numel() == n_blocks
+        np.save(os.path.join(tmpdir, f"counts{rank}.npy"), allc.numpy())
+    finally:
+        dist.destroy_process_group()
+
+
+@pytest.mark.parametrize("n_blocks", [101, 2, 1])
+def test_scatter_decode_gather_two_ranks(tmp_path, oracle, n_blocks):
+    """north_star's "NCCL only for the trivial block shard/gather": scatter a packed column from rank 0, decode per
+    rank, gather a small per-block result — ragged and degenerate shard sizes (one rank may own nothing)."""
+    import torch.multiprocessing as mp
+
+    width, world = 11, 2
+    mp.spawn(_scatter_worker, args=(world, _free_port(), n_blocks, width, str(tmp_path)), nprocs=world, join=True)
+    rng = np.random.default_rng(321)
+    packed = rng.integers(0, 1 << 31, size=n_blocks * 32 * width, dtype=np.int64).astype(np.int32).view(np.uint32)
+    want = (oracle.unpack(packed, width, n_blocks=n_blocks).reshape(n_blocks, 1024) < (1 << (width - 1))).sum(1)
+    for r in range(world):
+        assert np.array_equal(np.load(tmp_path / f"counts{r}.npy"), want.astype(np.int32))
