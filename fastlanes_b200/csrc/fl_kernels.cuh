@@ -336,37 +336,13 @@ __host__ __device__ constexpr int run_words() {
     return W == 0 ? 1 : (W == TB ? RPG : (RPG * W + TB - 1) / TB);
 }
 
-template <class T, int W, bool TMA, int RESERVE = 0>
-__device__ __forceinline__ void warp_load_run(const char* __restrict__ blk_packed, int lane, int q, int j,
-                                              Slice<T> (&a)[run_words<T, W>()]) {
+// Assembles the aligned run a[] of group rank q from a word-row loader (k -> this thread's 16-byte slice of word-row k).
+template <class T, int W, class Loader>
+__device__ __forceinline__ void warp_run_from(Loader&& load_word_row, int q, Slice<T> (&a)[run_words<T, W>()]) {
     using R = typename Lay<T>::R;
     constexpr int TB = Lay<T>::TB;
     constexpr int RPG = WarpLay<T>::RPG;
     constexpr int NR = Lay<T>::NR;
-    const char* pk = blk_packed + j * 16;
-
-    // word-row k of this block, this thread's 16-byte slice
-    constexpr bool USE_TMA = TMA && W > 0 && (kThreads / 32) * 128 * W + 128 + RESERVE <= 48 * 1024;  // static shared-memory limit (u64: W <= 47)
-    __shared__ __align__(128) unsigned char tma_buf[USE_TMA ? kThreads / 32 : 1][USE_TMA ? 128 * W : 16];
-    __shared__ __align__(8) unsigned long long tma_bar[USE_TMA ? kThreads / 32 : 1];
-    const unsigned char* sp = nullptr;
-    if constexpr (USE_TMA) {
-        const int wi = threadIdx.x >> 5;
-        const unsigned bar = smem_addr(&tma_bar[wi]);
-        if (lane == 0) mbar_init(bar, 1);
-        __syncwarp();
-        if (lane == 0) {
-            mbar_arrive_expect_tx(bar, 128 * W);
-            tma_bulk_load(smem_addr(&tma_buf[wi][0]), blk_packed, 128 * W, bar);
-        }
-        mbar_wait_parity(bar, 0);
-        sp = &tma_buf[wi][0] + j * 16;
-    }
-    auto load_word_row = [&](unsigned k) -> Slice<T> {
-        if constexpr (USE_TMA) return to_slice<T>(*reinterpret_cast<const uint4*>(sp + k * 128));
-        else return load_slice<T>(pk + k * 128);
-    };
-
     if constexpr (W == 0) {
         a[0] = slice_zero<T>();
     } else if constexpr (W == TB) {
@@ -401,6 +377,36 @@ __device__ __forceinline__ void warp_load_run(const char* __restrict__ blk_packe
             });
         }
     }
+}
+
+template <class T, int W, bool TMA, int RESERVE = 0>
+__device__ __forceinline__ void warp_load_run(const char* __restrict__ blk_packed, int lane, int q, int j,
+                                              Slice<T> (&a)[run_words<T, W>()]) {
+    const char* pk = blk_packed + j * 16;
+
+    // word-row k of this block, this thread's 16-byte slice
+    constexpr bool USE_TMA = TMA && W > 0 && (kThreads / 32) * 128 * W + 128 + RESERVE <= 48 * 1024;  // static shared-memory limit (u64: W <= 47)
+    __shared__ __align__(128) unsigned char tma_buf[USE_TMA ? kThreads / 32 : 1][USE_TMA ? 128 * W : 16];
+    __shared__ __align__(8) unsigned long long tma_bar[USE_TMA ? kThreads / 32 : 1];
+    const unsigned char* sp = nullptr;
+    if constexpr (USE_TMA) {
+        const int wi = threadIdx.x >> 5;
+        const unsigned bar = smem_addr(&tma_bar[wi]);
+        if (lane == 0) mbar_init(bar, 1);
+        __syncwarp();
+        if (lane == 0) {
+            mbar_arrive_expect_tx(bar, 128 * W);
+            tma_bulk_load(smem_addr(&tma_buf[wi][0]), blk_packed, 128 * W, bar);
+        }
+        mbar_wait_parity(bar, 0);
+        sp = &tma_buf[wi][0] + j * 16;
+    }
+    auto load_word_row = [&](unsigned k) -> Slice<T> {
+        if constexpr (USE_TMA) return to_slice<T>(*reinterpret_cast<const uint4*>(sp + k * 128));
+        else return load_slice<T>(pk + k * 128);
+    };
+
+    warp_run_from<T, W>(load_word_row, q, a);
 }
 
 template <class T, int W>
