@@ -36,6 +36,14 @@ def main():
         "transpose_delta_pack": lambda: _lib.fn("fl_transpose_delta_pack", tb)(w, n, U, B, P, sp),
         "unpack_filter": lambda: _lib.fn("fl_unpack_filter", tb)(w, n, P, None, 0, m // 4, m // 2, bm.data_ptr(), cnt.data_ptr(), sp),
     }
+    if op == "unpack_select":  # value-independent bitmap, ~25 % selected, + the exclusive prefix of the block counts
+        bm.view(torch.int32).random_(-(1 << 31), (1 << 31) - 1)
+        bm2 = bm.clone(); bm2.view(torch.int32).random_(-(1 << 31), (1 << 31) - 1)
+        bm &= bm2
+        c64 = torch.tensor([bin(i).count("1") for i in range(256)], dtype=torch.int64, device="cuda")[bm.long()].view(n, 128).sum(1)
+        offs = torch.cumsum(c64, 0) - c64
+        sel_out = torch.empty(int(c64.sum().item()) + 16, dtype=TDT[tb], device="cuda")
+        calls["unpack_select"] = lambda: _lib.fn("fl_unpack_select", tb)(w, n, P, None, 7, bm.data_ptr(), offs.data_ptr(), sel_out.data_ptr(), sp)
     for _ in range(5):
         assert calls[op]() == 0
     torch.cuda.synchronize()

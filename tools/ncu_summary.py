@@ -21,7 +21,8 @@ WANT = [
     "launch__grid_size", "launch__block_size", "launch__occupancy_limit_registers", "launch__waves_per_multiprocessor",
     "sm__cycles_elapsed.max", "smsp__cycles_active.avg", "sm__pipe_alu_cycles_active.avg.pct_of_peak_sustained_active",
     "smsp__warp_issue_stalled_long_scoreboard_per_warp_active.pct", "smsp__warp_issue_stalled_lg_throttle_per_warp_active.pct",
-    "smsp__average_warp_latency_issue_stalled_long_scoreboard.ratio",
+    "smsp__average_warp_latency_issue_stalled_long_scoreboard.ratio", "sm__issue_active.avg.pct_of_peak_sustained_elapsed",
+    "l1tex__throughput.avg.pct_of_peak_sustained_elapsed", "lts__throughput.avg.pct_of_peak_sustained_elapsed",
 ]
 
 
@@ -48,6 +49,8 @@ def main():
     traffic = json.load(open(tp)) if os.path.exists(tp) else {}
     captures = [(f"unpack u32 W={w} (headline kernel)", f"ncu_raw_unpack_u32_w{w}.csv", 128 * (w + 32) << 20, f"w{w}") for w in (1, 16, 32)]
     captures.append(("unpack_filter u32 W=8 (fused scan, lo<=v<=hi -> bitmap + counts)", "ncu_raw_filter_u32_w8.csv", (128 * 8 + 128 + 4) << 20, "filter_w8"))
+    captures.append(("unpack_select u32 W=8, 25 % selected (issue-bound: ~720 instructions per block)", "ncu_raw_select_u32_w8.csv",
+                     (128 * 8 + 128 + 8 + 4 * 256) << 20, "select_w8"))
     for title, fname, alg, label in captures:
         p = os.path.join(SRC, fname)
         if not os.path.exists(p):
