@@ -197,6 +197,19 @@ __device__ __forceinline__ T slice_lane(const Slice<T>& s, int k) {
     else return T(s.r[k >> 2] >> (8 * (k & 3)));
 }
 
+// predicated store: *p = v iff b != 0, as ONE predicated st.global (no branch around the store)
+template <class T>
+__device__ __forceinline__ void st_if(T* p, T v, uint32_t b) {
+    if constexpr (sizeof(T) == 8)
+        asm volatile("{\n .reg .pred q;\n setp.ne.u32 q, %2, 0;\n @q st.global.u64 [%0], %1;\n}" ::"l"(p), "l"(v), "r"(b) : "memory");
+    else if constexpr (sizeof(T) == 4)
+        asm volatile("{\n .reg .pred q;\n setp.ne.u32 q, %2, 0;\n @q st.global.u32 [%0], %1;\n}" ::"l"(p), "r"(v), "r"(b) : "memory");
+    else if constexpr (sizeof(T) == 2)
+        asm volatile("{\n .reg .pred q;\n setp.ne.u32 q, %2, 0;\n @q st.global.u16 [%0], %1;\n}" ::"l"(p), "h"(v), "r"(b) : "memory");
+    else
+        asm volatile("{\n .reg .pred q;\n setp.ne.u32 q, %2, 0;\n @q st.global.u8 [%0], %1;\n}" ::"l"(p), "r"(uint32_t(v)), "r"(b) : "memory");
+}
+
 template <class T, int W, bool TMA>
 __global__ void __launch_bounds__(kThreads)
 select_warp_kernel(const char* __restrict__ packed, const unsigned char* __restrict__ bitmap,
@@ -233,18 +246,21 @@ select_warp_kernel(const char* __restrict__ packed, const unsigned char* __restr
     warp_decode_tile<T, W, TMA, (kThreads / 32) * 256>(packed + blk * (size_t(128) * W), lane, q, j, v);
     const Slice<T> rs = slice_splat<T>(ref);
     T* o = out + obase;
+    asm volatile("" : "+l"(o));  // keep the block's output base as ONE 64-bit register: stores address it as o + 32-bit rank
 #pragma unroll
     for (int i = 0; i < RPG; ++i) {
         const int bit0 = row_bitmap_byte(q * RPG + i) * 8 + j * BPT;  // original index of this thread's first lane in row i
         const uint2 e = tile[bit0 >> 5];
         const int sh = bit0 & 31;
-        uint32_t bits = (e.x >> sh) & ((BPT == 32) ? 0xffffffffu : ((1u << BPT) - 1u));
-        if (bits == 0) continue;
-        uint32_t pos = e.y + uint32_t(__popc(e.x & ((1u << sh) - 1u)));
+        const uint32_t bits = (e.x >> sh) & ((BPT == 32) ? 0xffffffffu : ((1u << BPT) - 1u));
+        if (bits == 0) continue;  // nothing selected in this thread's slice of the row
+        uint32_t pos = e.y + uint32_t(__popc(e.x & ((1u << sh) - 1u)));  // rank of the slice's first selected value
         const Slice<T> val = slice_add<T>(v[i], rs);  // ffor.rs:47
 #pragma unroll
         for (int k = 0; k < BPT; ++k) {
-            if ((bits >> k) & 1u) o[pos++] = slice_lane<T>(val, k);
+            const uint32_t b = (bits >> k) & 1u;
+            st_if<T>(o + pos, slice_lane<T>(val, k), b);
+            pos += b;
         }
     }
 }

@@ -120,3 +120,37 @@ def test_config5_shard_wave_u32_w16(fl):
         expect = (words[:, row // 2, :] >> (16 * (row % 2))) & 0xFFFF
         start = order[row // 8] * 16 + (row % 8) * 128
         assert np.array_equal(got[:, start:start + 32], expect)
+
+
+def test_scan_full_size_u32(fl):
+    """Fused scan at configs[1] size (2^20 blocks, a few widths): bitmap popcounts == counts == the number of values of
+    the materialised unpack that satisfy the predicate (computed with torch on the device), per block; select returns
+    exactly those values in order."""
+    import torch
+
+    n = 1 << 20
+    bits = device_random_i32(n * 32 * 32, 42)
+    out = torch.empty(n * 1024, dtype=torch.int32, device="cuda")
+    bitmap = torch.empty(n * 128, dtype=torch.uint8, device="cuda")
+    counts = torch.empty(n, dtype=torch.int32, device="cuda")
+    for w, ref in ((3, 0), (13, 1000), (24, 0x7FFFFF00), (32, 12345)):
+        p = bits[: n * 32 * w]
+        fl.FoR.unfor_pack(w, p, ref, out)
+        lo = (ref + ((1 << w) - 1) // 5) & 0xFFFFFFFF
+        hi = (lo + ((1 << w) - 1) // 3) & 0xFFFFFFFF
+        fl.Scan.filter_range(w, p, ref, lo, hi, bitmap, counts)
+        v = out.to(torch.int64) & 0xFFFFFFFF
+        sel = (v >= lo) & (v <= hi) if lo <= hi else torch.zeros_like(v, dtype=torch.bool)
+        want = sel.view(n, 1024).sum(1).to(torch.int32)
+        assert torch.equal(counts, want), (w, "counts")
+        # bitmap bit i of block b <-> sel[b, i] (little-endian bit order), checked on the whole buffer
+        weights = (1 << torch.arange(8, device="cuda", dtype=torch.int32))
+        packed_bits = (sel.view(-1, 8).to(torch.int32) * weights).sum(1).to(torch.uint8)
+        assert torch.equal(bitmap, packed_bits), (w, "bitmap")
+        c64 = counts.to(torch.int64)
+        offsets = torch.cumsum(c64, 0) - c64
+        total = int(c64.sum().item())
+        dense = torch.empty(max(total, 1), dtype=torch.int32, device="cuda")
+        fl.Scan.select(w, p, ref, bitmap, offsets, dense)
+        assert torch.equal(dense[:total], out[sel.view(-1)]), (w, "select")
+        del v, sel, packed_bits, dense
