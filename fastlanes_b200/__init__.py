@@ -438,6 +438,36 @@ class Scan:
                                                                  hi_v, b.ptr, cptr))
 
     @staticmethod
+    def filter_range_delta(width: int, packed, base, lo, hi, bitmap, counts=None) -> None:
+        """Range scan over a delta-encoded column: bitmap bit i = lo <= untranspose(undelta_pack::<W>(packed, base))[i]
+        <= hi (src/delta.rs:48-63 then src/transpose.rs:18-22), i.e. in ORIGINAL value order.  `base`: LANES elements
+        per block as for Delta.undelta_pack."""
+        p, bs, b = _Arg(packed, "packed"), _Arg(base, "base"), _Arg(bitmap, "bitmap")
+        if b.tbits != 8:
+            raise FastLanesError(_lib.FL_ERR_LEN, "bitmap must be uint8")
+        dev = _same_space(p, bs)
+        if (b.device is not None) != dev:
+            raise FastLanesError(_lib.FL_ERR_NULL, "all buffers must be host arrays or all CUDA tensors")
+        _check_width(width, p.tbits)
+        if b.n % 128:
+            raise FastLanesError(_lib.FL_ERR_LEN, "bitmap must hold 128 bytes per block")
+        n = b.n // 128
+        _expect(p, n * packed_len(p.tbits, width), "Input")
+        _expect(bs, n * (1024 // p.tbits), "Base")
+        cptr = None
+        if counts is not None:
+            c = _Arg(counts, "counts")
+            if c.tbits != 32 or (c.device is not None) != dev:
+                raise FastLanesError(_lib.FL_ERR_LEN, "counts must be uint32 in the same memory space")
+            _expect(c, n, "Counts")
+            cptr = c.ptr
+        lo_v, hi_v = _ref_value(lo, p.tbits), _ref_value(hi, p.tbits)
+        if dev:
+            _lib.check(_lib.fn("fl_undelta_pack_filter", p.tbits)(width, n, p.ptr, bs.ptr, lo_v, hi_v, b.ptr, cptr, _stream()))
+        else:
+            _lib.check(_lib.fn("fl_host_undelta_pack_filter", p.tbits)(width, n, p.ptr, bs.ptr, lo_v, hi_v, b.ptr, cptr))
+
+    @staticmethod
     def select(width: int, packed, reference, bitmap, offsets, output) -> None:
         """Dense compaction (CUDA tensors): output[offsets[b] + k] = k-th selected value of block b in index order;
         `offsets` (uint64/int64 per block) = exclusive prefix sum of the per-block counts."""

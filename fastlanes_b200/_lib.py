@@ -30,6 +30,7 @@ _PER_TYPE = {
     "fl_block_minmax": "nppps".replace(" ", ""), "fl_host_block_minmax": "nppp",
     "fl_for_pack_auto": "wnpppps",
     "fl_unpack_filter": "wnpprrrpps", "fl_host_unpack_filter": "wnprrrpp", "fl_unpack_select": "wnpprppps",
+    "fl_undelta_pack_filter": "wnpprrpps", "fl_host_undelta_pack_filter": "wnpprrpp",
     "fl_transpose": "npps", "fl_untranspose": "npps",
     "fl_host_transpose": "npp", "fl_host_untranspose": "npp",
 }

@@ -351,11 +351,29 @@ fl_status device_select(unsigned width, size_t n_blocks, const T* packed, const 
     return FL_OK;
 }
 
+template <class T>
+fl_status device_delta_filter(unsigned width, size_t n_blocks, const T* packed, const T* base, T lo, T hi, uint8_t* bitmap,
+                              uint32_t* counts, cudaStream_t stream) {
+    if (width > sizeof(T) * 8) return fail(FL_ERR_WIDTH, "width exceeds the bit size of the element type");
+    if (n_blocks == 0) return FL_OK;
+    if (n_blocks > (size_t(1) << 40)) return fail(FL_ERR_LEN, "n_blocks too large");
+    if (!bitmap || !base || (width && !packed)) return fail(FL_ERR_NULL, "null pointer");
+    if ((width && !aligned16(packed)) || !aligned16(bitmap) || !aligned16(base))
+        return fail(FL_ERR_ALIGN, "device pointers must be 16-byte aligned");
+    LaunchArgs a;
+    a.in = packed; a.base = base; a.out = bitmap; a.counts = counts; a.flo = lo; a.fhi = hi;
+    a.n_blocks = n_blocks; a.width = width; a.stream = stream;
+    const cudaError_t e = flb::launch_delta_filter<T>(a);
+    if (e != cudaSuccess) return cuda_fail(e, "delta filter launch");
+    return FL_OK;
+}
+
 // host buffers: H2D of the packed chunk, filter kernel, D2H of 128 (+4) bytes per block — the decoded values never
 // cross the PCIe link
+// `base` != nullptr selects the delta scan (reference unused)
 template <class T>
-fl_status host_filter(unsigned width, size_t n_blocks, const T* packed, T reference, T lo, T hi, uint8_t* bitmap,
-                      uint32_t* counts) {
+fl_status host_filter(unsigned width, size_t n_blocks, const T* packed, const T* base, T reference, T lo, T hi,
+                      uint8_t* bitmap, uint32_t* counts) {
     if (width > sizeof(T) * 8) return fail(FL_ERR_WIDTH, "width exceeds the bit size of the element type");
     if (n_blocks == 0) return FL_OK;
     if (!bitmap || (width && !packed)) return fail(FL_ERR_NULL, "null pointer");
@@ -376,6 +394,7 @@ fl_status host_filter(unsigned width, size_t n_blocks, const T* packed, T refere
         if (!sl.stream) FL_CUDA(cudaStreamCreateWithFlags(&sl.stream, cudaStreamNonBlocking));
         if (ib) if (fl_status st = ensure(&sl.d_in, &sl.in_cap, cb * ib)) return st;
         if (fl_status st = ensure(&sl.d_out, &sl.out_cap, cb * 128 + cb * sizeof(uint32_t))) return st;
+        if (base) if (fl_status st = ensure(&sl.d_base, &sl.base_cap, cb * 128)) return st;
     }
     fl_status result = FL_OK;
     for (size_t c = 0; c < n_chunks && result == FL_OK; ++c) {
@@ -386,9 +405,15 @@ fl_status host_filter(unsigned width, size_t n_blocks, const T* packed, T refere
         uint32_t* d_counts = reinterpret_cast<uint32_t*>(d_bitmap + cb * 128);
         cudaError_t e = cudaSuccess;
         if (ib) e = cudaMemcpyAsync(sl.d_in, reinterpret_cast<const char*>(packed) + b0 * ib, nb * ib, cudaMemcpyHostToDevice, sl.stream);
+        if (e == cudaSuccess && base)
+            e = cudaMemcpyAsync(sl.d_base, reinterpret_cast<const char*>(base) + b0 * 128, nb * 128, cudaMemcpyHostToDevice, sl.stream);
         if (e != cudaSuccess) { result = cuda_fail(e, "cudaMemcpyAsync H2D"); break; }
-        result = device_filter<T>(width, nb, static_cast<const T*>(sl.d_in), nullptr, reference, lo, hi, d_bitmap,
-                                  counts ? d_counts : nullptr, sl.stream);
+        if (base)
+            result = device_delta_filter<T>(width, nb, static_cast<const T*>(sl.d_in), static_cast<const T*>(sl.d_base), lo, hi,
+                                            d_bitmap, counts ? d_counts : nullptr, sl.stream);
+        else
+            result = device_filter<T>(width, nb, static_cast<const T*>(sl.d_in), nullptr, reference, lo, hi, d_bitmap,
+                                      counts ? d_counts : nullptr, sl.stream);
         if (result != FL_OK) break;
         e = cudaMemcpyAsync(bitmap + b0 * 128, d_bitmap, nb * 128, cudaMemcpyDeviceToHost, sl.stream);
         if (e == cudaSuccess && counts)
@@ -647,7 +672,16 @@ fl_status fl_shutdown(void) {
     }                                                                                                                   \
     fl_status fl_host_unpack_filter_##SFX(unsigned width, size_t n, const T* packed, T reference, T lo, T hi,           \
                                           uint8_t* bitmap, uint32_t* counts) {                                          \
-        return host_filter<T>(width, n, packed, reference, lo, hi, bitmap, counts);                                     \
+        return host_filter<T>(width, n, packed, nullptr, reference, lo, hi, bitmap, counts);                            \
+    }                                                                                                                   \
+    fl_status fl_undelta_pack_filter_##SFX(unsigned width, size_t n, const T* packed, const T* base, T lo, T hi,        \
+                                           uint8_t* bitmap, uint32_t* counts, void* st) {                               \
+        return device_delta_filter<T>(width, n, packed, base, lo, hi, bitmap, counts, (cudaStream_t)st);                \
+    }                                                                                                                   \
+    fl_status fl_host_undelta_pack_filter_##SFX(unsigned width, size_t n, const T* packed, const T* base, T lo, T hi,   \
+                                                uint8_t* bitmap, uint32_t* counts) {                                    \
+        if (!base) return fail(FL_ERR_NULL, "null base pointer");                                                       \
+        return host_filter<T>(width, n, packed, base, 0, lo, hi, bitmap, counts);                                       \
     }                                                                                                                   \
     fl_status fl_unpack_select_##SFX(unsigned width, size_t n, const T* packed, const T* refs, T reference,             \
                                      const uint8_t* bitmap, const uint64_t* offsets, T* out, void* st) {                \

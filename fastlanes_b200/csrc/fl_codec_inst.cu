@@ -185,6 +185,23 @@ static cudaError_t do_select(const LaunchArgs& a) {
         a.n_blocks, static_cast<const T*>(a.refs), T(a.ref_scalar));
     return cudaGetLastError();
 }
+template <class T, int W>
+static cudaError_t do_delta_filter(const LaunchArgs& a) {
+    const unsigned grid = unsigned((a.n_blocks * 32 + kThreads - 1) / kThreads);
+    delta_filter_warp_kernel<T, W, false><<<grid, kThreads, 0, a.stream>>>(
+        static_cast<const char*>(a.in), static_cast<const char*>(a.base), static_cast<unsigned char*>(a.out), a.counts,
+        a.n_blocks, T(a.flo), T(a.fhi));
+    return cudaGetLastError();
+}
+template <class T, int... W>
+static constexpr std::array<launch_fn, sizeof...(W)> delta_filter_table(std::integer_sequence<int, W...>) {
+    return {{&do_delta_filter<T, W>...}};
+}
+template <>
+cudaError_t launch_delta_filter<elem_t>(const LaunchArgs& a) {
+    static constexpr auto tab = delta_filter_table<elem_t>(std::make_integer_sequence<int, Lay<elem_t>::TB + 1>{});
+    return tab[a.width](a);
+}
 template <class T, int... W>
 static constexpr std::array<launch_fn, sizeof...(W)> filter_table(std::integer_sequence<int, W...>) {
     return {{&do_filter<T, W>...}};

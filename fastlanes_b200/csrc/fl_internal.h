@@ -35,6 +35,7 @@ template <class T> cudaError_t launch_delta(bool undo, const LaunchArgs& a);
 template <class T> cudaError_t launch_transpose_warp(bool undo, const LaunchArgs& a);
 template <class T> cudaError_t launch_filter(const LaunchArgs& a);  // in = packed, out = bitmap
 template <class T> cudaError_t launch_select(const LaunchArgs& a);  // in = packed, out = dense values
+template <class T> cudaError_t launch_delta_filter(const LaunchArgs& a);  // in = packed, base, out = bitmap
 
 // Defined for all types in fl_misc.cu.
 template <class T> cudaError_t launch_transpose(bool undo, const LaunchArgs& a);

@@ -189,6 +189,90 @@ filter_warp_kernel(const char* __restrict__ packed, unsigned char* __restrict__ 
     }
 }
 
+// ---------------------------------------------------------------------------------------------------
+// Delta scan: bit i of the block's bitmap = lo <= untranspose(undelta_pack(packed, base))[i] <= hi — the range scan
+// over a delta-encoded (sorted ids, timestamps) column, answered in ORIGINAL value order without materialising the
+// decoded block (src/delta.rs:48-63 + src/transpose.rs:18-22 + the caller-side loop of README.md:40-41).
+// Decode and prefix-add exactly as unpack_warp_kernel<UOP_DELTA>; the predicate bits are kept lane-major so that
+// every thread owns whole bytes of the original-order bitmap (fl_scan_bits.h, "delta scan").
+// ---------------------------------------------------------------------------------------------------
+template <class T, int W, bool TMA>
+__global__ void __launch_bounds__(kThreads)
+delta_filter_warp_kernel(const char* __restrict__ packed, const char* __restrict__ base, unsigned char* __restrict__ bitmap,
+                         uint32_t* __restrict__ counts, size_t n_blocks, T lo, T hi) {
+    using R = typename Lay<T>::R;
+    using WL = WarpLay<T>;
+    constexpr int TB = Lay<T>::TB;
+    constexpr int RPG = WL::RPG;
+    constexpr int NR = Lay<T>::NR;
+    const size_t blk = (size_t(blockIdx.x) * kThreads + threadIdx.x) >> 5;
+    if (blk >= n_blocks) return;  // warp-uniform
+    const int lane = threadIdx.x & 31;
+    const int g = lane >> 3, j = lane & 7;
+    const int q = WL::rank_of_group(g);
+    Slice<T> carry = load_slice<T>(base + blk * 128 + j * 16);  // prev = base[lane] (delta.rs:50), before the TMA wait
+    Slice<T> v[RPG];
+    warp_decode_tile<T, W, TMA, (kThreads / 32) * 128>(packed + blk * (size_t(128) * W), lane, q, j, v);
+
+    // delta.rs:56-60: running wrapping sum along rows per lane (same as unpack_warp_kernel<UOP_DELTA>)
+#pragma unroll
+    for (int i = 1; i < RPG; ++i) v[i] = slice_add<T>(v[i], v[i - 1]);
+#pragma unroll
+    for (int qq = 0; qq < 3; ++qq) {  // totals of the runs that precede this one in row order
+        const int src = WL::group_of_rank(qq) * 8 + j;
+#pragma unroll
+        for (int r = 0; r < NR; ++r) {
+            const R t = shfl_reg<R>(v[RPG - 1].r[r], src);
+            if (qq < q) carry.r[r] = lane_add<T>(carry.r[r], t);
+        }
+    }
+#pragma unroll
+    for (int i = 0; i < RPG; ++i) v[i] = slice_add<T>(v[i], carry);
+
+    // lo <= value <= hi  <=>  (value - lo) mod 2^T <= hi - lo; bits LANE-major: bit k*RPG + i
+    uint32_t x = 0;
+    const Slice<T> cs = slice_splat<T>(lo), ss = slice_splat<T>(T(hi - lo));
+    const R c = cs.r[0], span = ss.r[0];
+    if constexpr (sizeof(T) >= 4) {
+        const R not_span = ~span;
+#pragma unroll
+        for (int r = NR - 1; r >= 0; --r)  // descending bit position: the last value shifted in lands at bit 0
+#pragma unroll
+            for (int i = RPG - 1; i >= 0; --i) shift_in_fail(x, R(v[i].r[r] - c), not_span);
+        x = ~x;
+    } else {
+        const R spanH = span | rep_value<T>(T(T(1) << (TB - 1)));
+        seq_rows<RPG>([&](auto ic) {
+            constexpr int i = decltype(ic)::value;
+#pragma unroll
+            for (int r = 0; r < 4; ++r) {
+                const uint32_t le = swar_leu_top<TB>(lane_sub<T>(v[i].r[r], c), span, spanH);
+                if constexpr (sizeof(T) == 2) x |= top_bits_lane_major_u16(le) << (8 * r + i);
+                else x |= top_bits_lane_major_u8(le) << (8 * r + i);
+            }
+        });
+    }
+    if (hi < lo) x = 0;  // empty range
+
+    __shared__ __align__(16) unsigned char scan_tile[kThreads / 32][128];
+    unsigned char* tile = scan_tile[threadIdx.x >> 5];
+    // u8 / u16: rank == group, so the thread holding the same lanes at rank q^1 (q^2) is lane^8 (lane^16)
+    if constexpr (sizeof(T) == 2) {
+        x = merge_pair_bpt4(x, __shfl_xor_sync(0xffffffffu, x, 8), q);
+    } else if constexpr (sizeof(T) == 1) {
+        x = merge_pair_bpt2(x, __shfl_xor_sync(0xffffffffu, x, 8), q);
+        x = merge_quad_bpt2(x, __shfl_xor_sync(0xffffffffu, x, 16), q);
+    }
+    scan_store_orig<TB>(tile, q, j, x);
+    __syncwarp();
+    const uint32_t word = reinterpret_cast<const uint32_t*>(tile)[lane];
+    reinterpret_cast<uint32_t*>(bitmap + blk * 128)[lane] = word;
+    if (counts != nullptr) {
+        const uint32_t n = __reduce_add_sync(0xffffffffu, uint32_t(__popc(word)));
+        if (lane == 0) counts[blk] = n;
+    }
+}
+
 // lane k (0 .. 16/sizeof(T) - 1) of a 16-byte slice
 template <class T>
 __device__ __forceinline__ T slice_lane(const Slice<T>& s, int k) {

@@ -103,4 +103,45 @@ FLB_HD void scan_store(unsigned char* tile, int q, int j, uint32_t z) {
     }
 }
 
+// ---- delta scan: bitmap in ORIGINAL value order --------------------------------------------------------------------
+// After undelta_pack the register tile is in transposed order: lane l walks, row by row, the T consecutive originals
+// start(l) .. start(l)+T-1, start(l) = 64*(l%16) + 8*FL_ORDER[l/16] (src/transpose.rs:29-36 composed with
+// src/macros.rs:20-24).  A thread's RPG rows of one lane are therefore RPG CONSECUTIVE bits of the original-order
+// bitmap, so its 32 predicate bits are kept LANE-major, bit k*RPG + i (k = lane inside the 16-byte slice, i = local
+// row): u32 -> 4 whole bytes, u64 -> 2 halfwords; u16 (4 bits per lane) / u8 (2 bits per lane) are completed to whole
+// bytes with the threads holding the same lanes in the neighbouring row groups (q^1, q^2) through the same
+// merge_pair / merge_quad helpers as above, with the group rank q in the role of j.
+
+// lane-major placement of the SWAR compare result of ONE register (top bit of each lane set = pass):
+// u8: lanes 4r..4r+3 -> bits 0,2,4,6 (stride RPG = 2);  u16: lanes 2r, 2r+1 -> bits 0, 4 (stride RPG = 4)
+FLB_HD uint32_t top_bits_lane_major_u8(uint32_t le) { return ((((le >> 7) & 0x01010101u) * 0x00041041u) >> 18) & 0x55u; }
+FLB_HD uint32_t top_bits_lane_major_u16(uint32_t le) {
+    const uint32_t z = (le >> 15) & 0x00010001u;  // bit 0, bit 16
+    return (z | (z >> 12)) & 0x11u;
+}
+
+// first original index (block-local) of lane l's run
+FLB_HD int lane_run_start(int l) { return 64 * (l & 15) + 8 * scan_fl_order(l >> 4); }
+
+// Stores a thread's assembled word of the ORIGINAL-order bitmap into the warp's 128-byte tile.  `z` is
+//   u32 : X itself (byte k = lane 4j+k, rows 8q..8q+7)            u64 : X itself (halfword k = lane 2j+k, rows 16q..16q+15)
+//   u16 : merge_pair_bpt4(X, X of rank q^1, q)  -> byte ii = lane 8j + 4(q&1) + ii, rows 8(q>>1) .. +7
+//   u8  : merge_quad_bpt2(merge_pair_bpt2(X, X of q^1, q), same of q^2, q) -> byte ii = lane 16j + 8(q&1) + 4(q>>1) + ii, rows 0..7
+template <int TBITS>
+FLB_HD void scan_store_orig(unsigned char* tile, int q, int j, uint32_t z) {
+    if (TBITS == 32) {
+        for (int k = 0; k < 4; ++k) tile[lane_run_start(4 * j + k) / 8 + q] = (unsigned char)(z >> (8 * k));
+    } else if (TBITS == 64) {
+        for (int k = 0; k < 2; ++k) {
+            unsigned char* p = tile + lane_run_start(2 * j + k) / 8 + 2 * q;
+            p[0] = (unsigned char)(z >> (16 * k));
+            p[1] = (unsigned char)(z >> (16 * k + 8));
+        }
+    } else if (TBITS == 16) {
+        for (int ii = 0; ii < 4; ++ii) tile[lane_run_start(8 * j + 4 * (q & 1) + ii) / 8 + (q >> 1)] = (unsigned char)(z >> (8 * ii));
+    } else {
+        for (int ii = 0; ii < 4; ++ii) tile[lane_run_start(16 * j + 8 * (q & 1) + 4 * (q >> 1) + ii) / 8] = (unsigned char)(z >> (8 * ii));
+    }
+}
+
 }  // namespace flb

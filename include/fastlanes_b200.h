@@ -149,6 +149,13 @@ FL_API fl_status fl_shutdown(void);
                                      T lo, T hi, uint8_t* bitmap, uint32_t* counts, void* stream);                  \
     FL_API fl_status fl_host_unpack_filter_##SFX(unsigned width, size_t n_blocks, const T* packed, T reference, T lo,      \
                                           T hi, uint8_t* bitmap, uint32_t* counts);                                 \
+    /* Delta scan: bit i = lo <= untranspose(undelta_pack(packed, base))[i] <= hi — the range scan over a delta-encoded   \
+     * column (src/delta.rs:48-63, src/transpose.rs:18-22), answered in ORIGINAL value order, block never materialised. \
+     * base: n_blocks * LANES elements as for fl_undelta_pack. */                                                       \
+    FL_API fl_status fl_undelta_pack_filter_##SFX(unsigned width, size_t n_blocks, const T* packed, const T* base, T lo,   \
+                                           T hi, uint8_t* bitmap, uint32_t* counts, void* stream);                  \
+    FL_API fl_status fl_host_undelta_pack_filter_##SFX(unsigned width, size_t n_blocks, const T* packed, const T* base,    \
+                                                T lo, T hi, uint8_t* bitmap, uint32_t* counts);                     \
     FL_API fl_status fl_unpack_select_##SFX(unsigned width, size_t n_blocks, const T* packed, const T* refs, T reference,  \
                                      const uint8_t* bitmap, const uint64_t* offsets, T* out, void* stream);         \
     /* Transpose::transpose / untranspose — src/transpose.rs:5-6 (impl :11-22) */                                   \

@@ -66,6 +66,56 @@ static int run(int trials) {
     return bad;
 }
 
+// delta scan: predicate given in ORIGINAL order; the warp holds it in transposed order (value (row, lane) of the
+// unpacked vector is original[t(index(row, lane))], src/transpose.rs:29-36), lane-major bits per thread.
+static int transpose_index(int i) { return (i % 16) * 64 + FL_ORDER[(i / 16) % 8] * 8 + i / 128; }
+
+template <int TBITS>
+static int run_orig(int trials) {
+    constexpr int RPG = TBITS / 4, BPT = 128 / TBITS;
+    int bad = 0;
+    for (int t = 0; t < trials; ++t) {
+        unsigned char pred[1024];
+        const int density = t % 5;
+        for (auto& p : pred) {
+            const uint64_t r = rnd();
+            p = density == 0 ? (r & 1) : density == 1 ? ((r & 31) == 0) : density == 2 ? ((r & 31) != 0) : density == 3;
+        }
+        unsigned char expect[128] = {0}, tile[128];
+        std::memset(tile, 0xAA, sizeof tile);
+        for (int i = 0; i < 1024; ++i) if (pred[i]) expect[i >> 3] |= (unsigned char)(1u << (i & 7));
+        uint32_t X[32], Y[32], Z[32];
+        int Q[32];
+        for (int th = 0; th < 32; ++th) {
+            const int g = th >> 3, j = th & 7;
+            const int q = (TBITS >= 32) ? (g == 1 ? 2 : (g == 2 ? 1 : g)) : g;
+            Q[th] = q;
+            uint32_t x = 0;
+            for (int k = 0; k < BPT; ++k)
+                for (int i = 0; i < RPG; ++i) {
+                    const int row = q * RPG + i, lane = j * BPT + k;
+                    const int idx = FL_ORDER[row / 8] * 16 + (row % 8) * 128 + lane;  // position in the unpacked vector
+                    if (pred[transpose_index(idx)]) x |= 1u << (k * RPG + i);
+                }
+            X[th] = x;
+        }
+        // u8 / u16: rank == group, so rank q^1 is thread th^8 and rank q^2 is thread th^16
+        for (int th = 0; th < 32; ++th) {
+            if (TBITS == 16) Z[th] = flb::merge_pair_bpt4(X[th], X[th ^ 8], Q[th]);
+            else if (TBITS == 8) Y[th] = flb::merge_pair_bpt2(X[th], X[th ^ 8], Q[th]);
+            else Z[th] = X[th];
+        }
+        if (TBITS == 8)
+            for (int th = 0; th < 32; ++th) Z[th] = flb::merge_quad_bpt2(Y[th], Y[th ^ 16], Q[th]);
+        for (int th = 0; th < 32; ++th) flb::scan_store_orig<TBITS>(tile, Q[th], th & 7, Z[th]);
+        if (std::memcmp(tile, expect, 128) != 0) {
+            if (!bad) std::printf("u%d trial %d: original-order bitmap mismatch\n", TBITS, t);
+            ++bad;
+        }
+    }
+    return bad;
+}
+
 int main() {
     int bad = 0;
     // SWAR lane-wise x <= y and the top-bit compression: u8 exhaustive over (x, y) in every lane position with
@@ -95,6 +145,21 @@ int main() {
             if (bits != want) { if (bad < 5) std::printf("u16 leu X=%08x Y=%08x got %x want %x\n", X, Y, bits, want); ++bad; }
         }
     }
+    // lane-major top-bit placement
+    for (int m = 0; m < 16; ++m) {
+        uint32_t le = (uint32_t)rnd() & 0x7F7F7F7Fu, want = 0;
+        for (int k = 0; k < 4; ++k) if (m >> k & 1) { le |= 0x80u << (8 * k); want |= 1u << (2 * k); }
+        if (flb::top_bits_lane_major_u8(le) != want) { std::printf("top_bits_lane_major_u8(%08x)\n", le); ++bad; }
+    }
+    for (int m = 0; m < 4; ++m) {
+        uint32_t le = (uint32_t)rnd() & 0x7FFF7FFFu, want = 0;
+        for (int k = 0; k < 2; ++k) if (m >> k & 1) { le |= 0x8000u << (16 * k); want |= 1u << (4 * k); }
+        if (flb::top_bits_lane_major_u16(le) != want) { std::printf("top_bits_lane_major_u16(%08x)\n", le); ++bad; }
+    }
+    bad += run_orig<8>(200);
+    bad += run_orig<16>(200);
+    bad += run_orig<32>(200);
+    bad += run_orig<64>(200);
     bad += run<8>(200);
     bad += run<16>(200);
     bad += run<32>(200);

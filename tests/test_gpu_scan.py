@@ -185,3 +185,60 @@ def test_for_pack_auto_every_width(fl, oracle, tb):
         fits = (v2.max(1) - v2.min(1)).astype(np.uint64) <= np.uint64(mask(w))
         got = to_host(out, tb).reshape(n, 1024)
         assert np.array_equal(got[fits], v2[fits]), (tb, w, "round trip of the lossless blocks")
+
+
+@pytest.mark.parametrize("tb", [8, 16, 32, 64])
+def test_delta_filter_every_width(fl, oracle, tb):
+    """Delta scan: bitmap of lo <= untranspose(undelta_pack(packed, base)) <= hi in ORIGINAL order (src/delta.rs:48-63,
+    src/transpose.rs:18-22), device and host families, against the oracle composition."""
+    import torch
+
+    rng = np.random.default_rng(1300 + tb)
+    n = N_BLOCKS
+    full = mask(tb)
+    for w in range(tb + 1):
+        packed = rand_bytes(rng, n * 128 * w, tb)
+        base = rand_bytes(rng, n * 128, tb)
+        values = oracle.untranspose(oracle.undelta_pack(packed, base, w, n_blocks=n))
+        v0 = int(values[rng.integers(0, values.size)])
+        for lo, hi in ((full // 4, full // 4 * 3), (v0, v0), (9, 3), (0, full), (full - full // 7, full)):
+            want, sel = expected_bitmap(values, lo, hi)
+            bitmap = torch.full((n * 128,), 0x5A, dtype=torch.uint8, device="cuda")
+            counts = torch.full((n,), -1, dtype=torch.int32, device="cuda")
+            fl.Scan.filter_range_delta(w, to_dev(packed), to_dev(base), lo, hi, bitmap, counts)
+            assert np.array_equal(bitmap.cpu().numpy(), want), (tb, w, lo, hi)
+            assert np.array_equal(counts.cpu().numpy().view(np.uint32), sel.reshape(n, 1024).sum(1).astype(np.uint32)), (tb, w)
+        if w in (0, 1, tb // 2, tb):  # host family
+            h_bitmap = np.zeros(n * 128, dtype=np.uint8)
+            h_counts = np.zeros(n, dtype=np.uint32)
+            fl.Scan.filter_range_delta(w, packed, base, full // 3, full // 3 * 2, h_bitmap, h_counts)
+            want, sel = expected_bitmap(values, full // 3, full // 3 * 2)
+            assert np.array_equal(h_bitmap, want), (tb, w, "host")
+            assert np.array_equal(h_counts, sel.reshape(n, 1024).sum(1).astype(np.uint32))
+
+
+def test_delta_filter_sorted_column_u64(fl, oracle):
+    """The use case: a sorted u64 column (timestamps) delta-encoded block by block with the reference's own chain
+    transpose -> delta -> pack (src/delta.rs:88-95, here the fused encoder), scanned for a time range."""
+    import torch
+
+    rng = np.random.default_rng(99)
+    n, w = 513, 20
+    steps = rng.integers(0, 1 << w, size=n * 1024, dtype=np.uint64)
+    ts = np.uint64(1_700_000_000_000) + np.cumsum(steps, dtype=np.uint64)
+    # base[lane] = the value preceding the lane's run: u64 lane l walks originals 64*l .. 64*l+63 (SURVEY.md App. A), so
+    # its base is the column value just before original 64*l (the running predecessor across block boundaries)
+    prev = np.concatenate([[ts[0] - steps[0]], ts[:-1]]).reshape(n, 1024)
+    base = prev[:, ::64].reshape(-1).copy()
+    d_packed = dev_empty(n * 16 * w, 64)
+    fl.Delta.transpose_delta_pack(w, to_dev(ts), to_dev(base), d_packed)
+    back = dev_empty(n * 1024, 64)
+    fl.Delta.undelta_pack_untranspose(w, d_packed, to_dev(base), back)
+    assert np.array_equal(to_host(back, 64), ts), "encode/decode chain does not round-trip"
+    lo, hi = int(ts[n * 300]), int(ts[n * 700])
+    bitmap = torch.empty(n * 128, dtype=torch.uint8, device="cuda")
+    counts = torch.empty(n, dtype=torch.int32, device="cuda")
+    fl.Scan.filter_range_delta(w, d_packed, to_dev(base), lo, hi, bitmap, counts)
+    want, sel = expected_bitmap(ts, lo, hi)
+    assert np.array_equal(bitmap.cpu().numpy(), want)
+    assert int(counts.sum().item()) == int(sel.sum())

@@ -74,13 +74,17 @@ def main():
                 rec("transpose_delta_pack", w, 128 * (w + tb + 1), lambda: _lib.fn("fl_transpose_delta_pack", tb)(w, n, U, B, P, sp))
         # fused scan: filter = decode + range predicate -> 128-byte bitmap + count per block;
         # select = decode + compaction of the selected values (here ~25 % selected by a value-independent bitmap)
-        if not only or (only & {"unpack_filter", "unpack_select_25pct"}):
+        if not only or (only & {"unpack_filter", "unpack_select_25pct", "undelta_pack_filter"}):
+            full = (1 << tb) - 1
             bm = torch.empty(n * 128, dtype=torch.uint8, device="cuda")
             cnt = torch.empty(n, dtype=torch.int32, device="cuda")
             for w in widths:
                 lo, hi = ((1 << w) - 1) // 4, ((1 << w) - 1) // 2
                 rec("unpack_filter", w, 128 * w + 128 + 4,
                     lambda: _lib.fn("fl_unpack_filter", tb)(w, n, P, None, 0, lo, hi, bm.data_ptr(), cnt.data_ptr(), sp))
+            for w in widths:
+                rec("undelta_pack_filter", w, 128 * w + 128 + 128 + 4,
+                    lambda: _lib.fn("fl_undelta_pack_filter", tb)(w, n, P, B, full // 4, full // 2, bm.data_ptr(), cnt.data_ptr(), sp))
             bm.view(torch.int32).random_(-(1 << 31), (1 << 31) - 1)
             bm2 = bm.clone(); bm2.view(torch.int32).random_(-(1 << 31), (1 << 31) - 1)
             bm &= bm2  # density 1/4
