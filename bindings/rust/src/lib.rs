@@ -194,6 +194,9 @@ pub mod device {
         /// pass).  bitmap: 128 bytes per block, bit i = lo <= unfor_pack(packed, reference)[i] <= hi; counts nullable.
         pub fn fl_unpack_filter_u32(width: u32, n_blocks: usize, packed: *const u32, refs: *const u32, reference: u32,
                                     lo: u32, hi: u32, bitmap: *mut u8, counts: *mut u32, stream: *mut c_void) -> i32;
+        /// Delta scan: bit i = lo <= untranspose(undelta_pack(packed, base))[i] <= hi (original value order).
+        pub fn fl_undelta_pack_filter_u32(width: u32, n_blocks: usize, packed: *const u32, base: *const u32, lo: u32, hi: u32,
+                                          bitmap: *mut u8, counts: *mut u32, stream: *mut c_void) -> i32;
         /// Dense compaction of the selected values: out[offsets[b] + k] = k-th selected value of block b.
         pub fn fl_unpack_select_u32(width: u32, n_blocks: usize, packed: *const u32, refs: *const u32, reference: u32,
                                     bitmap: *const u8, offsets: *const u64, out: *mut u32, stream: *mut c_void) -> i32;

@@ -44,6 +44,7 @@ template <class T> struct Abi;
         static fl_status undelta_pack_untranspose(unsigned w, size_t n, const T* i, const T* b, T* o) { return fl_host_undelta_pack_untranspose_##SFX(w, n, i, b, o); } \
         static fl_status transpose_delta_pack(unsigned w, size_t n, const T* i, const T* b, T* o) { return fl_host_transpose_delta_pack_##SFX(w, n, i, b, o); } \
         static fl_status filter(unsigned w, size_t n, const T* i, T r, T lo, T hi, uint8_t* bm, uint32_t* c) { return fl_host_unpack_filter_##SFX(w, n, i, r, lo, hi, bm, c); } \
+        static fl_status delta_filter(unsigned w, size_t n, const T* i, const T* b, T lo, T hi, uint8_t* bm, uint32_t* c) { return fl_host_undelta_pack_filter_##SFX(w, n, i, b, lo, hi, bm, c); } \
         static fl_status transpose(size_t n, const T* i, T* o) { return fl_host_transpose_##SFX(n, i, o); }     \
         static fl_status untranspose(size_t n, const T* i, T* o) { return fl_host_untranspose_##SFX(n, i, o); } \
     };
@@ -148,6 +149,14 @@ struct Scan {
         static_assert(W <= FastLanes<T>::T_BITS, "BitPackWidth<W>: SupportedBitPackWidth<T>");
         uint32_t count = 0;
         detail::check(detail::Abi<T>::filter(W, 1, input.data(), reference, lo, hi, bitmap.data(), &count), "filter_range");
+        return count;
+    }
+    // bit i = lo <= untranspose(undelta_pack::<W>(input, base))[i] <= hi  (src/delta.rs:48-63, src/transpose.rs:18-22)
+    template <std::size_t W>
+    static uint32_t filter_range_delta(const Packed<T, W>& input, const typename Delta<T>::Base& base, T lo, T hi, Bitmap& bitmap) {
+        static_assert(W <= FastLanes<T>::T_BITS, "BitPackWidth<W>: SupportedBitPackWidth<T>");
+        uint32_t count = 0;
+        detail::check(detail::Abi<T>::delta_filter(W, 1, input.data(), base.data(), lo, hi, bitmap.data(), &count), "filter_range_delta");
         return count;
     }
 };

@@ -103,6 +103,25 @@ int main() {
         }
         EXPECT(count == want);
     }
+    {   // delta scan == untranspose(undelta_pack) + predicate loop, on test_delta's data (src/delta.rs:81-107)
+        constexpr std::size_t W = 15;
+        std::array<uint16_t, 1024> values{}, transposed{}, deltas{};
+        for (std::size_t i = 0; i < 1024; ++i) values[i] = uint16_t(i / 8);
+        Transpose<uint16_t>::transpose(values, transposed);
+        Delta<uint16_t>::Base base{};
+        Delta<uint16_t>::delta(transposed, base, deltas);
+        Packed<uint16_t, W> packed{};
+        BitPacking<uint16_t>::pack<W>(deltas, packed);
+        Scan<uint16_t>::Bitmap bitmap{};
+        const uint32_t count = Scan<uint16_t>::filter_range_delta<W>(packed, base, 17, 99, bitmap);
+        uint32_t want = 0;
+        for (std::size_t i = 0; i < 1024; ++i) {
+            const bool sel = values[i] >= 17 && values[i] <= 99;
+            want += sel;
+            EXPECT(bool((bitmap[i / 8] >> (i % 8)) & 1) == sel);
+        }
+        EXPECT(count == want);
+    }
     {   // index >= 1024 panics (src/bitpacking.rs:152)
         Packed<uint16_t, 3> packed{};
         bool threw = false;
