@@ -389,17 +389,21 @@ def main():
     launches = args.steps * len(WIDTHS)
 
     # ---- per-width kernel durations (roofline), same K, events around each launch ------------
+    # Two passes of K launches per width; per width the pass with the smaller MEAN is kept (one stray 3 ms launch —
+    # seen once next to the nvidia-smi sampler — would otherwise define a whole width).
     per_w_ms, per_w_med = {}, {}
-    for w in WIDTHS:
-        evs = []
-        for _ in range(args.steps):
-            a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-            a.record(stream); launch(w); b.record(stream)
-            evs.append((a, b))
-        torch.cuda.synchronize()
-        ts = [a.elapsed_time(b) for a, b in evs]
-        per_w_ms[w] = statistics.mean(ts)
-        per_w_med[w] = statistics.median(ts)
+    for _pass in range(2):
+        for w in WIDTHS:
+            evs = []
+            for _ in range(args.steps):
+                a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+                a.record(stream); launch(w); b.record(stream)
+                evs.append((a, b))
+            torch.cuda.synchronize()
+            ts = [a.elapsed_time(b) for a, b in evs]
+            if w not in per_w_ms or statistics.mean(ts) < per_w_ms[w]:
+                per_w_ms[w] = statistics.mean(ts)
+                per_w_med[w] = statistics.median(ts)
     if rank == 0:
         time.sleep(0.2)
         sampler.stop()
@@ -422,6 +426,7 @@ def main():
         "achieved": round(achieved, 1), "peak": peak, "unit": "GB/s", "frac": round(achieved / peak, 4),
         "peak_source": peak_src, "traffic": None,
         "algorithmic_bytes_per_launch": "128*(W+32) bytes/block * 2^%d blocks" % args.log2_blocks,
+        "timing": "CUDA events around each launch on the launching stream; per width the mean of K launches, better of 2 passes",
         "min_frac_over_widths": round(per_width[str(worst)]["GBps"] / peak, 4), "min_frac_width": worst,
         "per_width": per_width,
     }

@@ -401,9 +401,8 @@ class Scan:
     bit i%8 (numpy `packbits(bitorder="little")`)."""
 
     @staticmethod
-    def filter_range(width: int, packed, reference, lo, hi, bitmap, counts=None) -> None:
-        """bitmap bit i = lo <= value[i] <= hi (unsigned, inclusive).  `reference`: scalar, or (CUDA tensors) one
-        per block.  `counts` (optional, uint32 per block) receives the number of selected values."""
+    def _bitmap_args(width: int, packed, bitmap, counts):
+        """Common plumbing: (packed arg, bitmap arg, on_device, n_blocks, counts pointer or None)."""
         p, b = _Arg(packed, "packed"), _Arg(bitmap, "bitmap")
         if b.tbits != 8:
             raise FastLanesError(_lib.FL_ERR_LEN, "bitmap must be uint8")
@@ -422,16 +421,27 @@ class Scan:
                 raise FastLanesError(_lib.FL_ERR_LEN, "counts must be uint32 in the same memory space")
             _expect(c, n, "Counts")
             cptr = c.ptr
+        return p, b, dev, n, cptr
+
+    @staticmethod
+    def _reference_args(reference, p: _Arg, n: int):
+        """(per-block references pointer or None, scalar reference)."""
+        if _is_torch(reference) and reference.dim() > 0:
+            r = _Arg(reference, "reference")
+            if r.tbits != p.tbits or r.device is None:
+                raise FastLanesError(_lib.FL_ERR_LEN, "per-block references: a CUDA tensor of the packed element type")
+            _expect(r, n, "Reference")
+            return r.ptr, 0
+        return None, _ref_value(reference, p.tbits)
+
+    @staticmethod
+    def filter_range(width: int, packed, reference, lo, hi, bitmap, counts=None) -> None:
+        """bitmap bit i = lo <= value[i] <= hi (unsigned, inclusive).  `reference`: scalar, or (CUDA tensors) one
+        per block.  `counts` (optional, uint32 per block) receives the number of selected values."""
+        p, b, dev, n, cptr = Scan._bitmap_args(width, packed, bitmap, counts)
         lo_v, hi_v = _ref_value(lo, p.tbits), _ref_value(hi, p.tbits)
         if dev:
-            if _is_torch(reference) and reference.dim() > 0:
-                r = _Arg(reference, "reference")
-                if r.tbits != p.tbits:
-                    raise FastLanesError(_lib.FL_ERR_LEN, "all buffers must share one element type")
-                _expect(r, n, "Reference")
-                rptr, rval = r.ptr, 0
-            else:
-                rptr, rval = None, _ref_value(reference, p.tbits)
+            rptr, rval = Scan._reference_args(reference, p, n)
             _lib.check(_lib.fn("fl_unpack_filter", p.tbits)(width, n, p.ptr, rptr, rval, lo_v, hi_v, b.ptr, cptr, _stream()))
         else:
             _lib.check(_lib.fn("fl_host_unpack_filter", p.tbits)(width, n, p.ptr, _ref_value(reference, p.tbits), lo_v,
@@ -442,25 +452,10 @@ class Scan:
         """Range scan over a delta-encoded column: bitmap bit i = lo <= untranspose(undelta_pack::<W>(packed, base))[i]
         <= hi (src/delta.rs:48-63 then src/transpose.rs:18-22), i.e. in ORIGINAL value order.  `base`: LANES elements
         per block as for Delta.undelta_pack."""
-        p, bs, b = _Arg(packed, "packed"), _Arg(base, "base"), _Arg(bitmap, "bitmap")
-        if b.tbits != 8:
-            raise FastLanesError(_lib.FL_ERR_LEN, "bitmap must be uint8")
-        dev = _same_space(p, bs)
-        if (b.device is not None) != dev:
-            raise FastLanesError(_lib.FL_ERR_NULL, "all buffers must be host arrays or all CUDA tensors")
-        _check_width(width, p.tbits)
-        if b.n % 128:
-            raise FastLanesError(_lib.FL_ERR_LEN, "bitmap must hold 128 bytes per block")
-        n = b.n // 128
-        _expect(p, n * packed_len(p.tbits, width), "Input")
+        p, b, dev, n, cptr = Scan._bitmap_args(width, packed, bitmap, counts)
+        bs = _Arg(base, "base")
+        _same_space(p, bs)
         _expect(bs, n * (1024 // p.tbits), "Base")
-        cptr = None
-        if counts is not None:
-            c = _Arg(counts, "counts")
-            if c.tbits != 32 or (c.device is not None) != dev:
-                raise FastLanesError(_lib.FL_ERR_LEN, "counts must be uint32 in the same memory space")
-            _expect(c, n, "Counts")
-            cptr = c.ptr
         lo_v, hi_v = _ref_value(lo, p.tbits), _ref_value(hi, p.tbits)
         if dev:
             _lib.check(_lib.fn("fl_undelta_pack_filter", p.tbits)(width, n, p.ptr, bs.ptr, lo_v, hi_v, b.ptr, cptr, _stream()))
@@ -471,23 +466,14 @@ class Scan:
     def select(width: int, packed, reference, bitmap, offsets, output) -> None:
         """Dense compaction (CUDA tensors): output[offsets[b] + k] = k-th selected value of block b in index order;
         `offsets` (uint64/int64 per block) = exclusive prefix sum of the per-block counts."""
-        p, b, f, o = _Arg(packed, "packed"), _Arg(bitmap, "bitmap"), _Arg(offsets, "offsets"), _Arg(output, "output")
-        if None in (p.device, b.device, f.device, o.device):
+        p, b, dev, n, _ = Scan._bitmap_args(width, packed, bitmap, None)
+        f, o = _Arg(offsets, "offsets"), _Arg(output, "output")
+        if not dev or f.device is None or o.device is None:
             raise FastLanesError(_lib.FL_ERR_NULL, "select takes CUDA tensors")
-        if b.tbits != 8 or f.tbits != 64 or o.tbits != p.tbits:
-            raise FastLanesError(_lib.FL_ERR_LEN, "bitmap must be uint8, offsets 64-bit, output of the packed element type")
-        _check_width(width, p.tbits)
-        if b.n % 128:
-            raise FastLanesError(_lib.FL_ERR_LEN, "bitmap must hold 128 bytes per block")
-        n = b.n // 128
-        _expect(p, n * packed_len(p.tbits, width), "Input")
+        if f.tbits != 64 or o.tbits != p.tbits:
+            raise FastLanesError(_lib.FL_ERR_LEN, "offsets must be 64-bit, output of the packed element type")
         _expect(f, n, "Offsets")
-        if _is_torch(reference) and reference.dim() > 0:
-            r = _Arg(reference, "reference")
-            _expect(r, n, "Reference")
-            rptr, rval = r.ptr, 0
-        else:
-            rptr, rval = None, _ref_value(reference, p.tbits)
+        rptr, rval = Scan._reference_args(reference, p, n)
         _lib.check(_lib.fn("fl_unpack_select", p.tbits)(width, n, p.ptr, rptr, rval, b.ptr, f.ptr, o.ptr, _stream()))
 
 

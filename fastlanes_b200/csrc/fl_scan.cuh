@@ -77,13 +77,20 @@ __device__ __forceinline__ void shift_in_fail(uint32_t& acc, uint64_t t, uint64_
     asm("{\n .reg .u64 d;\n add.cc.u64 d, %1, %2;\n addc.u32 %0, %0, %0;\n}" : "+r"(acc) : "l"(t), "l"(not_span));
 }
 
-// Block-invariant part of the predicate for one FoR reference (per block only when `refs` is given).
+// Block-invariant part of the predicate for one FoR reference (per block only when `refs` is given).  Three modes:
+//   IN_PLACE   u32/u64, W > 0     field compared inside the packed word (see the kernel); p0 = -(A << k), p1 = ~bound
+//   SWAR_FIELD u8/u16, 0 < W < T  the extracted values are < 2^W <= H = 2^(T-1), so the top bit of every SWAR lane is
+//                                  free and A <= v <= B needs no carry isolation: top(v + (H - A)) & top((H | B) - v);
+//                                  p0 = splat(H - A), p1 = splat(H | B)
+//   GENERIC    W == 0, or u8/u16 at W == T: (v - c) <= span lane-wise; p0 = c, p1 = span, p2 = span | H
+// `invert`: IN_PLACE / SWAR_FIELD: XOR mask of the result (range_in_field); GENERIC: ~0 when the range is empty.
 template <class T, int W>
 struct FilterPred {
     using R = typename Lay<T>::R;
     static constexpr bool IN_PLACE = sizeof(T) >= 4 && W > 0;
-    R p0, p1, p2;      // IN_PLACE: neg_a, not_bound, -      else: c, span, span | H
-    uint32_t invert;   // IN_PLACE: XOR mask of the result   else: ~0 when the range is empty (hi < lo)
+    static constexpr bool SWAR_FIELD = sizeof(T) <= 2 && W > 0 && W < Lay<T>::TB;
+    R p0, p1, p2;
+    uint32_t invert;
     __device__ __forceinline__ FilterPred(T ref, T lo, T hi) {
         constexpr int TB = Lay<T>::TB;
         if constexpr (IN_PLACE) {
@@ -91,6 +98,13 @@ struct FilterPred {
             constexpr int k = TB - W;
             p0 = R(0) - R(fr.a << k);
             p1 = ~R(R(R(fr.b - fr.a) << k) | R((R(1) << k) - 1));
+            p2 = 0;
+            invert = fr.invert;
+        } else if constexpr (SWAR_FIELD) {
+            constexpr T H = T(T(1) << (TB - 1));
+            const FieldRange<T> fr = range_in_field<T>(T(lo - ref), T(hi - lo), hi < lo, T((T(1) << W) - 1));  // mod 2^T
+            p0 = slice_splat<T>(T(H - fr.a)).r[0];
+            p1 = slice_splat<T>(T(H | fr.b)).r[0];
             p2 = 0;
             invert = fr.invert;
         } else {
@@ -161,14 +175,27 @@ filter_warp_kernel(const char* __restrict__ packed, unsigned char* __restrict__ 
             const R c = pred.p0, span = pred.p1;
             if constexpr (sizeof(T) >= 4) {  // W == 0: every value is 0
                 x = (R(R(0) - c) <= span) ? 0xffffffffu : 0u;
+                x &= ~pred.invert;  // empty range
+            } else if constexpr (FilterPred<T, W>::SWAR_FIELD) {
+                constexpr R H = rep_value<T>(T(T(1) << (TB - 1)));
+                seq_rows<RPG>([&](auto ic) {
+                    constexpr int i = decltype(ic)::value;
+#pragma unroll
+                    for (int r = 0; r < 4; ++r) {
+                        const uint32_t top = (v[i].r[r] + c) & (span - v[i].r[r]) & H;  // c = splat(H - A), span = splat(H | B)
+                        if constexpr (sizeof(T) == 2) x |= top_bits_u16(top) << (i * BPT + 2 * r);
+                        else x |= top_bits_u8(top) << (i * BPT + 4 * r);
+                    }
+                });
+                x ^= pred.invert;
             } else {
                 const R spanH = pred.p2;
                 seq_rows<RPG>([&](auto ic) {
                     constexpr int i = decltype(ic)::value;
                     slice_range_bits<T, i * BPT>(x, v[i], c, span, spanH);
                 });
+                x &= ~pred.invert;  // empty range
             }
-            x &= ~pred.invert;  // empty range
         }
 
         if constexpr (sizeof(T) == 4) {

@@ -15,5 +15,11 @@ timeout 600 ncu --set full --clock-control none --import-source on -k regex:filt
     python tools/ncu_one.py unpack_filter 32 8 > gpurun_out/ncu_filter_w8.log 2>&1; echo "ncu filter exit $?"
 ncu -i /tmp/prof_filter_u32_w8.ncu-rep --page raw --csv > gpurun_out/ncu_raw_filter_u32_w8.csv 2>/dev/null
 ncu -i /tmp/prof_filter_u32_w8.ncu-rep --page source --csv > gpurun_out/ncu_source_filter_u32_w8.csv 2>/dev/null
+timeout 600 ncu --set full --clock-control none -k regex:select_warp_kernel -s 2 -c 1 -f -o /tmp/prof_select_u32_w8 \
+    python tools/ncu_one.py unpack_select 32 8 > gpurun_out/ncu_select_w8.log 2>&1; echo "ncu select exit $?"
+ncu -i /tmp/prof_select_u32_w8.ncu-rep --page raw --csv > gpurun_out/ncu_raw_select_u32_w8.csv 2>/dev/null
+CS=/usr/local/cuda/bin/compute-sanitizer
+timeout 1200 $CS --tool memcheck --error-exitcode 9 python -m pytest tests/test_gpu_scan.py tests/test_gpu_parity.py tests/test_golden.py -q -m gpu -x > gpurun_out/sanitizer_memcheck_s2.txt 2>&1; echo "memcheck exit $?" | tee -a gpurun_out/sanitizer_memcheck_s2.txt
+timeout 1200 $CS --tool racecheck --error-exitcode 9 python -m pytest tests/test_gpu_scan.py -q -m gpu -x -k "filter_every_width or select_every_width or pipeline or for_pack_auto or delta_filter" > gpurun_out/sanitizer_racecheck_s2.txt 2>&1; echo "racecheck exit $?" | tee -a gpurun_out/sanitizer_racecheck_s2.txt
 timeout 900 python tools/opbench.py > gpurun_out/opbench_s2.log 2>&1; echo "opbench exit $?"; tail -3 gpurun_out/opbench_s2.log
 du -sh gpurun_out
