@@ -62,6 +62,17 @@ def test_gpu_reproduces_golden(gold):
         assert np.array_equal(u, gold[f"u{tb}_w{w}_undelta_pack"]), (tb, w, "undelta_pack")
         fl.FoR.unfor_pack(w, p, ref, u)
         assert np.array_equal(u, gold[f"u{tb}_w{w}_unfor_pack"]), (tb, w, "unfor_pack")
+        # fused scans against the golden decoded arrays: FoR domain (index order) and Delta domain (original order)
+        full = (1 << tb) - 1
+        lo, hi = full // 4, full // 4 * 3
+        bitmap = np.zeros(2 * 128, dtype=np.uint8)
+        fl.Scan.filter_range(w, p, ref, lo, hi, bitmap)
+        g = gold[f"u{tb}_w{w}_unfor_pack"]
+        assert np.array_equal(bitmap, np.packbits((g >= DT[tb](lo)) & (g <= DT[tb](hi)), bitorder="little")), (tb, w, "filter")
+        fl.Scan.filter_range_delta(w, p, base, lo, hi, bitmap)
+        g = np.zeros_like(v)
+        fl.Transpose.untranspose(gold[f"u{tb}_w{w}_undelta_pack"], g)
+        assert np.array_equal(bitmap, np.packbits((g >= DT[tb](lo)) & (g <= DT[tb](hi)), bitorder="little")), (tb, w, "delta filter")
     for tb in (8, 16, 32, 64):
         v = gold[f"u{tb}_values"]
         t = np.zeros_like(v)
