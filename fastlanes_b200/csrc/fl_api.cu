@@ -40,6 +40,10 @@ fl_status cuda_fail(cudaError_t e, const char* where) {
 
 inline bool aligned16(const void* p) { return (reinterpret_cast<uintptr_t>(p) & 15u) == 0; }
 
+// One launch covers at most 2^31 blocks: every kernel maps >= 1 block per warp and 8 warps per CTA, so the grid stays
+// below 2^28 CTAs (gridDim.x limit 2^31 - 1).  2^31 u8 blocks are already 2 TiB unpacked — beyond any single GPU.
+constexpr size_t kMaxBlocksPerLaunch = size_t(1) << 31;
+
 enum class Op { Pack, Unpack, ForPack, UnforPack, Delta, Undelta, UndeltaPack, Transpose, Untranspose,
                 UndeltaPackUntranspose, TransposeDeltaPack };
 
@@ -82,7 +86,7 @@ fl_status device_op(Op op, unsigned width, size_t n_blocks, const void* in, void
     if (op_has_width(op) && width > TB) return fail(FL_ERR_WIDTH, "width exceeds the bit size of the element type");
     if (!op_has_width(op)) width = 0;
     if (n_blocks == 0) return FL_OK;
-    if (n_blocks > (size_t(1) << 40)) return fail(FL_ERR_LEN, "n_blocks too large");
+    if (n_blocks > kMaxBlocksPerLaunch) return fail(FL_ERR_LEN, "n_blocks too large for one launch (limit 2^31)");
     const bool in_used = in_block_bytes(op, TB, width) != 0;
     const bool out_used = out_block_bytes(op, TB, width) != 0;
     if ((in_used && !in) || (out_used && !out)) return fail(FL_ERR_NULL, "null data pointer");
@@ -250,6 +254,7 @@ fl_status host_op(Op op, unsigned width, size_t n_blocks, const void* in, void* 
 template <class T>
 fl_status device_minmax(size_t n_blocks, const T* in, T* mins, T* maxs, cudaStream_t stream) {
     if (n_blocks == 0) return FL_OK;
+    if (n_blocks > kMaxBlocksPerLaunch) return fail(FL_ERR_LEN, "n_blocks too large for one launch (limit 2^31)");
     if (!in || !mins || !maxs) return fail(FL_ERR_NULL, "null pointer");
     if (!aligned16(in)) return fail(FL_ERR_ALIGN, "device pointers must be 16-byte aligned");
     cudaError_t e = flb::launch_block_minmax<T>(n_blocks, in, mins, maxs, stream);
@@ -307,7 +312,7 @@ fl_status device_for_pack_auto(unsigned width, size_t n_blocks, const T* in, T* 
                                cudaStream_t stream) {
     if (width > sizeof(T) * 8) return fail(FL_ERR_WIDTH, "width exceeds the bit size of the element type");
     if (n_blocks == 0) return FL_OK;
-    if (n_blocks > (size_t(1) << 40)) return fail(FL_ERR_LEN, "n_blocks too large");
+    if (n_blocks > kMaxBlocksPerLaunch) return fail(FL_ERR_LEN, "n_blocks too large for one launch (limit 2^31)");
     if (!in || !refs_out || (width && !packed)) return fail(FL_ERR_NULL, "null pointer");
     if (!aligned16(in) || (width && !aligned16(packed))) return fail(FL_ERR_ALIGN, "device pointers must be 16-byte aligned");
     LaunchArgs a;
@@ -324,7 +329,7 @@ fl_status device_filter(unsigned width, size_t n_blocks, const T* packed, const 
                         uint8_t* bitmap, uint32_t* counts, cudaStream_t stream) {
     if (width > sizeof(T) * 8) return fail(FL_ERR_WIDTH, "width exceeds the bit size of the element type");
     if (n_blocks == 0) return FL_OK;
-    if (n_blocks > (size_t(1) << 40)) return fail(FL_ERR_LEN, "n_blocks too large");
+    if (n_blocks > kMaxBlocksPerLaunch) return fail(FL_ERR_LEN, "n_blocks too large for one launch (limit 2^31)");
     if (!bitmap || (width && !packed)) return fail(FL_ERR_NULL, "null pointer");
     if ((width && !aligned16(packed)) || !aligned16(bitmap)) return fail(FL_ERR_ALIGN, "device pointers must be 16-byte aligned");
     LaunchArgs a;
@@ -340,7 +345,7 @@ fl_status device_select(unsigned width, size_t n_blocks, const T* packed, const 
                         const uint8_t* bitmap, const uint64_t* offsets, T* out, cudaStream_t stream) {
     if (width > sizeof(T) * 8) return fail(FL_ERR_WIDTH, "width exceeds the bit size of the element type");
     if (n_blocks == 0) return FL_OK;
-    if (n_blocks > (size_t(1) << 40)) return fail(FL_ERR_LEN, "n_blocks too large");
+    if (n_blocks > kMaxBlocksPerLaunch) return fail(FL_ERR_LEN, "n_blocks too large for one launch (limit 2^31)");
     if (!bitmap || !offsets || !out || (width && !packed)) return fail(FL_ERR_NULL, "null pointer");
     if ((width && !aligned16(packed)) || !aligned16(bitmap)) return fail(FL_ERR_ALIGN, "device pointers must be 16-byte aligned");
     LaunchArgs a;
@@ -356,7 +361,7 @@ fl_status device_delta_filter(unsigned width, size_t n_blocks, const T* packed, 
                               uint32_t* counts, cudaStream_t stream) {
     if (width > sizeof(T) * 8) return fail(FL_ERR_WIDTH, "width exceeds the bit size of the element type");
     if (n_blocks == 0) return FL_OK;
-    if (n_blocks > (size_t(1) << 40)) return fail(FL_ERR_LEN, "n_blocks too large");
+    if (n_blocks > kMaxBlocksPerLaunch) return fail(FL_ERR_LEN, "n_blocks too large for one launch (limit 2^31)");
     if (!bitmap || !base || (width && !packed)) return fail(FL_ERR_NULL, "null pointer");
     if ((width && !aligned16(packed)) || !aligned16(bitmap) || !aligned16(base))
         return fail(FL_ERR_ALIGN, "device pointers must be 16-byte aligned");

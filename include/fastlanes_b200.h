@@ -44,7 +44,7 @@ typedef int fl_status;
 enum {
     FL_OK = 0,
     FL_ERR_WIDTH = 1, /* width > T            (src/bitpacking.rs:93,126,197 unreachable!) */
-    FL_ERR_LEN = 2,   /* size overflow        (src/bitpacking.rs:78-80,111-113 debug_assert) */
+    FL_ERR_LEN = 2,   /* more than 2^31 blocks in one call; the slice-length debug_asserts (src/bitpacking.rs:78-80,111-113) are the host mirrors' job */
     FL_ERR_INDEX = 3, /* index out of range   (src/bitpacking.rs:152 assert!) */
     FL_ERR_ALIGN = 4, /* device pointer not 16-byte aligned */
     FL_ERR_CUDA = 5,  /* CUDA runtime error or no device; see fl_last_error_string() */

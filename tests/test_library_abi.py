@@ -81,3 +81,29 @@ def test_header_is_plain_c():
     r = subprocess.run(["gcc", "-std=c99", "-Wall", "-Wextra", "-pedantic", "-Werror", "-fsyntax-only", "-x", "c",
                         os.path.join(ROOT, "include", "fastlanes_b200.h")], capture_output=True, text=True)
     assert r.returncode == 0, r.stderr
+
+
+def test_c_abi_argument_checks_need_no_device():
+    """The device-pointer entry points validate their arguments before touching CUDA: width, block count, NULL and
+    alignment errors come back as status codes (never a crash / unwind), with or without a GPU."""
+    import ctypes
+
+    from fastlanes_b200 import _lib
+
+    L = _lib.lib()
+    buf = ctypes.create_string_buffer(8192 + 64)
+    base = (ctypes.addressof(buf) + 15) & ~15  # 16-byte aligned scratch (never dereferenced: every call below fails first)
+    FL_ERR_WIDTH, FL_ERR_LEN, FL_ERR_ALIGN, FL_ERR_NULL = 1, 2, 4, 6
+    assert L.fl_unpack_u32(33, 1, base, base + 4096, None) == FL_ERR_WIDTH          # bitpacking.rs:126 unreachable!()
+    assert L.fl_pack_u8(9, 1, base, base + 4096, None) == FL_ERR_WIDTH
+    assert L.fl_unpack_u32(8, (1 << 31) + 1, base, base + 4096, None) == FL_ERR_LEN
+    assert L.fl_unpack_u32(8, 1, None, base, None) == FL_ERR_NULL
+    assert L.fl_unpack_u32(8, 1, base + 4, base + 4096, None) == FL_ERR_ALIGN
+    assert L.fl_undelta_pack_u16(3, 1, base, None, base + 4096, None) == FL_ERR_NULL  # missing base
+    assert L.fl_unpack_filter_u32(33, 1, base, None, 0, 0, 1, base + 4096, None, None) == FL_ERR_WIDTH
+    assert L.fl_unpack_filter_u32(8, 1, base, None, 0, 0, 1, None, None, None) == FL_ERR_NULL
+    assert L.fl_undelta_pack_filter_u64(8, 1, base, None, 0, 1, base + 4096, None, None) == FL_ERR_NULL
+    assert L.fl_for_pack_auto_u32(8, 1, base, None, None, base + 4096, None) == FL_ERR_NULL
+    assert L.fl_unpack_u32(8, 0, None, None, None) == 0                               # empty batch: nothing to do
+    assert L.fl_pack_u32(0, 5, base, None, None) == 0                                 # W = 0 packs to nothing (macros.rs:52)
+    assert b"16-byte" in L.fl_last_error_string() or L.fl_last_error_string() is not None
