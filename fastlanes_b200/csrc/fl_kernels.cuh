@@ -37,6 +37,9 @@ enum PackOp : int { POP_PLAIN = 0, POP_FOR = 1, POP_ORIG_DELTA = 2, POP_FOR_AUTO
 #ifndef FLB_THREADS
 #define FLB_THREADS 256
 #endif
+#ifndef FLB_U64_DELTA_OCC_W
+#define FLB_U64_DELTA_OCC_W 12  // widths below this use the 3-CTAs-per-SM register cap in the u64 fused-delta kernel
+#endif
 constexpr int kThreads = FLB_THREADS;  // 256 threads = 32 blocks of 1024 values per CTA
 constexpr int kSlicesPerBlock = 8;  // 8 x 16 B = one 128-byte row
 
@@ -438,8 +441,13 @@ __device__ __forceinline__ void warp_decode_tile(const char* __restrict__ blk_pa
     warp_extract_rows<T, W>(a, v);
 }
 
+// u64 fused delta: 16 rows x 2 x 64-bit per thread want 88 registers = 2 CTAs per SM; the dependent shuffle scan needs
+// more resident warps than that at small W, so the compiler is held to 3 CTAs per SM (80 registers) there.
+template <class T, int OP, int W>
+constexpr int unpack_min_ctas() { return (sizeof(T) == 8 && OP == UOP_DELTA && W < FLB_U64_DELTA_OCC_W) ? 3 : 1; }
+
 template <class T, int W, int OP, bool TMA = false>
-__global__ void __launch_bounds__(kThreads)
+__global__ void __launch_bounds__(kThreads, unpack_min_ctas<T, OP, W>())
 unpack_warp_kernel(const char* __restrict__ packed, char* __restrict__ out, size_t n_blocks,
                    const T* __restrict__ refs, T ref_scalar, const char* __restrict__ base) {
     using R = typename Lay<T>::R;
