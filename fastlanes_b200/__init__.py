@@ -29,7 +29,7 @@ from ._lib import FastLanesError, LIB_PATH, exported_symbols  # noqa: F401
 
 FL_ORDER = (0, 4, 2, 6, 1, 5, 3, 7)  # src/lib.rs:22
 
-__all__ = ["BitPacking", "FoR", "Delta", "Transpose", "Scan", "FastLanes", "FastLanesError", "FL_ORDER",
+__all__ = ["BitPacking", "FoR", "Delta", "Transpose", "Scan", "Cwida", "FastLanes", "FastLanesError", "FL_ORDER",
            "packed_len", "version", "device_count", "init", "host_configure", "pinned_empty", "shutdown"]
 
 
@@ -475,6 +475,43 @@ class Scan:
         _expect(f, n, "Offsets")
         rptr, rval = Scan._reference_args(reference, p, n)
         _lib.check(_lib.fn("fl_unpack_select", p.tbits)(width, n, p.ptr, rptr, rval, b.ptr, f.ptr, o.ptr, _stream()))
+
+
+class Cwida:
+    """Bit-packing and FoR in the row order of the ORIGINAL cwida/FastLanes layout: row r of a
+    block holds values r*LANES .. r*LANES+LANES-1, where the reference crate visits rows in FL_ORDER-transposed order
+    and is therefore "not binary compatible with original FastLanes" (README.md:49-56, src/macros.rs:1-9).  Same
+    argument conventions as BitPacking / FoR; CUDA tensors only.  Parity unpinned: see oracle/cwida.py."""
+
+    @staticmethod
+    def _io(width, unpacked, packed, what_unpacked, what_packed):
+        u, p = _Arg(unpacked, what_unpacked), _Arg(packed, what_packed)
+        if not _same_space(u, p):
+            raise FastLanesError(_lib.FL_ERR_NULL, "the cwida entry points take CUDA tensors")
+        _check_width(width, u.tbits)
+        n = _n_blocks_unpacked(u, what_unpacked.capitalize())
+        _expect(p, n * packed_len(u.tbits, width), what_packed.capitalize())
+        return u, p, n
+
+    @staticmethod
+    def pack(width: int, input, output) -> None:
+        u, p, n = Cwida._io(width, input, output, "input", "output")
+        _call("fl_pack_cwida", u.tbits, True, width, n, u.ptr, p.ptr)
+
+    @staticmethod
+    def unpack(width: int, input, output) -> None:
+        u, p, n = Cwida._io(width, output, input, "output", "input")
+        _call("fl_unpack_cwida", u.tbits, True, width, n, p.ptr, u.ptr)
+
+    @staticmethod
+    def for_pack(width: int, input, reference, output) -> None:
+        u, p, n = Cwida._io(width, input, output, "input", "output")
+        _call("fl_for_pack_cwida", u.tbits, True, width, n, u.ptr, _ref_value(reference, u.tbits), p.ptr)
+
+    @staticmethod
+    def unfor_pack(width: int, input, reference, output) -> None:
+        u, p, n = Cwida._io(width, output, input, "output", "input")
+        _call("fl_unfor_pack_cwida", u.tbits, True, width, n, p.ptr, _ref_value(reference, u.tbits), u.ptr)
 
 
 _lib.lib()  # fail loudly at import time if the CUDA library is missing

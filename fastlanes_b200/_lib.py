@@ -28,6 +28,7 @@ _PER_TYPE = {
     "fl_undelta_pack_untranspose": "wnppps", "fl_host_undelta_pack_untranspose": "wnppp",
     "fl_transpose_delta_pack": "wnppps", "fl_host_transpose_delta_pack": "wnppp",
     "fl_block_minmax": "nppps".replace(" ", ""), "fl_host_block_minmax": "nppp",
+    "fl_pack_cwida": "wnpps", "fl_unpack_cwida": "wnpps", "fl_for_pack_cwida": "wnprps", "fl_unfor_pack_cwida": "wnprps",
     "fl_for_pack_auto": "wnpppps",
     "fl_unpack_filter": "wnpprrrpps", "fl_host_unpack_filter": "wnprrrpp", "fl_unpack_select": "wnpprppps",
     "fl_undelta_pack_filter": "wnpprrpps", "fl_host_undelta_pack_filter": "wnpprrpp",

@@ -45,16 +45,21 @@ inline bool aligned16(const void* p) { return (reinterpret_cast<uintptr_t>(p) & 
 constexpr size_t kMaxBlocksPerLaunch = size_t(1) << 31;
 
 enum class Op { Pack, Unpack, ForPack, UnforPack, Delta, Undelta, UndeltaPack, Transpose, Untranspose,
-                UndeltaPackUntranspose, TransposeDeltaPack };
+                UndeltaPackUntranspose, TransposeDeltaPack,
+                PackLinear, UnpackLinear, ForPackLinear, UnforPackLinear };  // cwida row order (linear rows)
 
 inline bool op_has_width(Op op) {
     return op == Op::Pack || op == Op::Unpack || op == Op::ForPack || op == Op::UnforPack || op == Op::UndeltaPack ||
-           op == Op::UndeltaPackUntranspose || op == Op::TransposeDeltaPack;
+           op == Op::UndeltaPackUntranspose || op == Op::TransposeDeltaPack || op == Op::PackLinear ||
+           op == Op::UnpackLinear || op == Op::ForPackLinear || op == Op::UnforPackLinear;
 }
 inline bool op_input_packed(Op op) {
-    return op == Op::Unpack || op == Op::UnforPack || op == Op::UndeltaPack || op == Op::UndeltaPackUntranspose;
+    return op == Op::Unpack || op == Op::UnforPack || op == Op::UndeltaPack || op == Op::UndeltaPackUntranspose ||
+           op == Op::UnpackLinear || op == Op::UnforPackLinear;
 }
-inline bool op_output_packed(Op op) { return op == Op::Pack || op == Op::ForPack || op == Op::TransposeDeltaPack; }
+inline bool op_output_packed(Op op) {
+    return op == Op::Pack || op == Op::ForPack || op == Op::TransposeDeltaPack || op == Op::PackLinear || op == Op::ForPackLinear;
+}
 inline bool op_has_base(Op op) {
     return op == Op::Delta || op == Op::Undelta || op == Op::UndeltaPack || op == Op::UndeltaPackUntranspose ||
            op == Op::TransposeDeltaPack;
@@ -107,6 +112,10 @@ fl_status device_op(Op op, unsigned width, size_t n_blocks, const void* in, void
         case Op::UndeltaPack: e = flb::launch_unpack<T>(flb::kUnpackDelta, a); break;
         case Op::UndeltaPackUntranspose: e = flb::launch_unpack<T>(flb::kUnpackDeltaOrig, a); break;
         case Op::TransposeDeltaPack: e = flb::launch_pack<T>(flb::kPackOrigDelta, a); break;
+        case Op::PackLinear: e = flb::launch_pack<T>(flb::kPackPlainLinear, a); break;
+        case Op::ForPackLinear: e = flb::launch_pack<T>(flb::kPackForLinear, a); break;
+        case Op::UnpackLinear: e = flb::launch_unpack<T>(flb::kUnpackPlainLinear, a); break;
+        case Op::UnforPackLinear: e = flb::launch_unpack<T>(flb::kUnpackForLinear, a); break;
         case Op::Delta: e = flb::launch_delta<T>(false, a); break;
         case Op::Undelta: e = flb::launch_delta<T>(true, a); break;
         case Op::Transpose: e = transpose_variant() ? flb::launch_transpose_warp<T>(false, a) : flb::launch_transpose<T>(false, a); break;
@@ -666,6 +675,18 @@ fl_status fl_shutdown(void) {
     }                                                                                                                   \
     fl_status fl_host_block_minmax_##SFX(size_t n, const T* in, T* mins, T* maxs) {                                     \
         return host_minmax<T>(n, in, mins, maxs);                                                                       \
+    }                                                                                                                   \
+    fl_status fl_pack_cwida_##SFX(unsigned width, size_t n, const T* in, T* packed, void* st) {                         \
+        return device_op<T>(Op::PackLinear, width, n, in, packed, nullptr, nullptr, 0, (cudaStream_t)st);               \
+    }                                                                                                                   \
+    fl_status fl_unpack_cwida_##SFX(unsigned width, size_t n, const T* packed, T* out, void* st) {                      \
+        return device_op<T>(Op::UnpackLinear, width, n, packed, out, nullptr, nullptr, 0, (cudaStream_t)st);            \
+    }                                                                                                                   \
+    fl_status fl_for_pack_cwida_##SFX(unsigned width, size_t n, const T* in, T reference, T* packed, void* st) {        \
+        return device_op<T>(Op::ForPackLinear, width, n, in, packed, nullptr, nullptr, reference, (cudaStream_t)st);    \
+    }                                                                                                                   \
+    fl_status fl_unfor_pack_cwida_##SFX(unsigned width, size_t n, const T* packed, T reference, T* out, void* st) {     \
+        return device_op<T>(Op::UnforPackLinear, width, n, packed, out, nullptr, nullptr, reference, (cudaStream_t)st); \
     }                                                                                                                   \
     fl_status fl_for_pack_auto_##SFX(unsigned width, size_t n, const T* in, T* refs_out, T* spans_out, T* packed,       \
                                      void* st) {                                                                       \

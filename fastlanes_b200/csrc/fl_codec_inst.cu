@@ -90,6 +90,19 @@ template <class T, int OP, int... W>
 static constexpr std::array<launch_fn, sizeof...(W)> unpack_table(std::integer_sequence<int, W...>) {
     return {{&do_unpack<T, W, OP>...}};
 }
+// cwida row order (linear rows; bit-packing and FoR only): same kernel, LINEAR = true, same load-path choice
+template <class T, int W, int OP>
+static cudaError_t do_unpack_linear(const LaunchArgs& a) {
+    const unsigned grid = unsigned((a.n_blocks * 32 + kThreads - 1) / kThreads);
+    unpack_warp_kernel<T, W, OP, (sizeof(T) >= 2), true><<<grid, kThreads, 0, a.stream>>>(
+        static_cast<const char*>(a.in), static_cast<char*>(a.out), a.n_blocks, static_cast<const T*>(a.refs),
+        T(a.ref_scalar), nullptr);
+    return cudaGetLastError();
+}
+template <class T, int OP, int... W>
+static constexpr std::array<launch_fn, sizeof...(W)> unpack_linear_table(std::integer_sequence<int, W...>) {
+    return {{&do_unpack_linear<T, W, OP>...}};
+}
 // fused undelta_pack + untranspose (all four types)
 template <class T>
 static cudaError_t unpack_delta_orig(const LaunchArgs& a) {
@@ -103,6 +116,11 @@ cudaError_t launch_unpack<elem_t>(int op, const LaunchArgs& a) {
     static constexpr auto ffor = unpack_table<elem_t, UOP_FOR>(seq{});
     static constexpr auto delta = unpack_table<elem_t, UOP_DELTA>(seq{});
     if (op == kUnpackDeltaOrig) return unpack_delta_orig<elem_t>(a);
+    if (op == kUnpackPlainLinear || op == kUnpackForLinear) {
+        static constexpr auto lplain = unpack_linear_table<elem_t, UOP_PLAIN>(seq{});
+        static constexpr auto lfor = unpack_linear_table<elem_t, UOP_FOR>(seq{});
+        return (op == kUnpackPlainLinear ? lplain : lfor)[a.width](a);
+    }
     switch (op) {
         case kUnpackPlain: return plain[a.width](a);
         case kUnpackFor: return ffor[a.width](a);
@@ -137,6 +155,23 @@ template <class T, int OP, int... W>
 static constexpr std::array<launch_fn, sizeof...(W)> pack_table(std::integer_sequence<int, W...>) {
     return {{&do_pack<T, W, OP>...}};
 }
+// cwida row order (linear rows)
+template <class T, int W, int OP>
+static cudaError_t do_pack_linear(const LaunchArgs& a) {
+    const unsigned grid = unsigned((a.n_blocks * 32 + kThreads - 1) / kThreads);
+    constexpr bool kTma = sizeof(T) >= 2;
+    const size_t smem = kTma ? size_t(kThreads / 32) * (128 * Lay<T>::TB + 8) : 0;
+    static const cudaError_t attr = cudaFuncSetAttribute(pack_warp_kernel<T, W, OP, kTma, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, int(smem));
+    if (attr != cudaSuccess) return attr;
+    pack_warp_kernel<T, W, OP, kTma, true><<<grid, kThreads, smem, a.stream>>>(
+        static_cast<const char*>(a.in), static_cast<char*>(a.out), a.n_blocks, static_cast<const T*>(a.refs),
+        T(a.ref_scalar), nullptr, nullptr, nullptr);
+    return cudaGetLastError();
+}
+template <class T, int OP, int... W>
+static constexpr std::array<launch_fn, sizeof...(W)> pack_linear_table(std::integer_sequence<int, W...>) {
+    return {{&do_pack_linear<T, W, OP>...}};
+}
 // fused transpose + delta + pack (all four types)
 template <class T>
 static cudaError_t pack_orig_delta(const LaunchArgs& a) {
@@ -156,6 +191,11 @@ cudaError_t launch_pack<elem_t>(int op, const LaunchArgs& a) {
     static constexpr auto ffor = pack_table<elem_t, POP_FOR>(seq{});
     if (op == kPackOrigDelta) return pack_orig_delta<elem_t>(a);
     if (op == kPackForAuto) return pack_for_auto<elem_t>(a);
+    if (op == kPackPlainLinear || op == kPackForLinear) {
+        static constexpr auto lplain = pack_linear_table<elem_t, POP_PLAIN>(seq{});
+        static constexpr auto lfor = pack_linear_table<elem_t, POP_FOR>(seq{});
+        return (op == kPackPlainLinear ? lplain : lfor)[a.width](a);
+    }
     if (op == kPackPlain) return plain[a.width](a);
     if (op == kPackFor) return ffor[a.width](a);
     return cudaErrorNotSupported;

@@ -25,8 +25,8 @@ struct LaunchArgs {
 };
 
 // op codes of launch_unpack / launch_pack (match UnpackOp / PackOp in fl_kernels.cuh)
-enum : int { kUnpackPlain = 0, kUnpackFor = 1, kUnpackDelta = 2, kUnpackDeltaOrig = 3 };
-enum : int { kPackPlain = 0, kPackFor = 1, kPackOrigDelta = 2, kPackForAuto = 3 };
+enum : int { kUnpackPlain = 0, kUnpackFor = 1, kUnpackDelta = 2, kUnpackDeltaOrig = 3, kUnpackPlainLinear = 4, kUnpackForLinear = 5 };
+enum : int { kPackPlain = 0, kPackFor = 1, kPackOrigDelta = 2, kPackForAuto = 3, kPackPlainLinear = 4, kPackForLinear = 5 };
 
 // Defined once per element type in fl_codec_inst.cu (compiled with -DFLB_TBITS=8/16/32/64).
 template <class T> cudaError_t launch_unpack(int op, const LaunchArgs& a);

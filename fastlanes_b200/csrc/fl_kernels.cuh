@@ -172,10 +172,14 @@ template <int RPG>
 __host__ __device__ constexpr int warp_visit_row(int ii) { return (RPG == 16) ? ((ii & 1) * 8 + (ii >> 1)) : ii; }
 
 // byte offset of local row i of the run of rank q (global row r = q*RPG + i), see row_byte_offset()
-template <class T, int I>
+// LINEAR = the row order of the original cwida/FastLanes bit-packing (row r = values r*LANES .. r*LANES+LANES-1, i.e.
+// byte offset r*128), which this crate reorders (README.md:49-56, src/macros.rs:1-9).
+template <class T, int I, bool LINEAR = false>
 __device__ __forceinline__ int warp_row_offset(int q) {
     constexpr int RPG = WarpLay<T>::RPG;
-    if constexpr (RPG >= 8) {
+    if constexpr (LINEAR) {
+        return (q * RPG + I) * 128;
+    } else if constexpr (RPG >= 8) {
         const int oidx = q * (RPG / 8) + I / 8;  // r/8 ; r%8 = I%8
         return (fl_order_rt(oidx) * 16 + (I % 8) * 128) * int(sizeof(T));
     } else {
@@ -446,7 +450,7 @@ __device__ __forceinline__ void warp_decode_tile(const char* __restrict__ blk_pa
 template <class T, int OP, int W>
 constexpr int unpack_min_ctas() { return (sizeof(T) == 8 && OP == UOP_DELTA && W < FLB_U64_DELTA_OCC_W) ? 3 : 1; }
 
-template <class T, int W, int OP, bool TMA = false>
+template <class T, int W, int OP, bool TMA = false, bool LINEAR = false>
 __global__ void __launch_bounds__(kThreads, unpack_min_ctas<T, OP, W>())
 unpack_warp_kernel(const char* __restrict__ packed, char* __restrict__ out, size_t n_blocks,
                    const T* __restrict__ refs, T ref_scalar, const char* __restrict__ base) {
@@ -459,7 +463,8 @@ unpack_warp_kernel(const char* __restrict__ packed, char* __restrict__ out, size
     if (blk >= n_blocks) return;  // warp-uniform
     const int lane = threadIdx.x & 31;
     const int g = lane >> 3, j = lane & 7;
-    const int q = WL::rank_of_group(g);
+    static_assert(!LINEAR || OP == UOP_PLAIN || OP == UOP_FOR, "cwida row order: bit-packing and FoR only");
+    const int q = LINEAR ? g : WL::rank_of_group(g);  // linear rows: groups in row order
     char* o = out + blk * (size_t(128) * TB) + j * 16;
 
     // prev = base[lane] (delta.rs:50): issued before the decode's TMA wait
@@ -511,7 +516,9 @@ unpack_warp_kernel(const char* __restrict__ packed, char* __restrict__ out, size
         constexpr int i = warp_visit_row<RPG>(decltype(ic)::value);
         // global row r = q*RPG + i: offset (FL_ORDER[r/8]*16 + (r%8)*128)*sizeof(T)  (macros.rs:20-24)
         int off;
-        if constexpr (RPG >= 8) {
+        if constexpr (LINEAR) {
+            off = (q * RPG + i) * 128;  // row r at byte r*128
+        } else if constexpr (RPG >= 8) {
             // r/8 = q*(RPG/8) + i/8 ; r%8 = i%8
             const int oidx = q * (RPG / 8) + i / 8;
             off = (fl_order_rt(oidx) * 16 + (i % 8) * 128) * int(sizeof(T));
@@ -531,7 +538,7 @@ unpack_warp_kernel(const char* __restrict__ packed, char* __restrict__ out, size
 // higher-rank group owns a shared word.
 // ---------------------------------------------------------------------------------------------------
 // TMA = true (plain / FoR ops): the 128*T-byte unpacked block arrives with one cp.async.bulk per warp.
-template <class T, int W, int OP, bool TMA = false>
+template <class T, int W, int OP, bool TMA = false, bool LINEAR = false>
 __global__ void __launch_bounds__(kThreads)
 pack_warp_kernel(const char* __restrict__ in, char* __restrict__ packed, size_t n_blocks,
                  const T* __restrict__ refs, T ref_scalar, const char* __restrict__ base,
@@ -546,7 +553,8 @@ pack_warp_kernel(const char* __restrict__ in, char* __restrict__ packed, size_t 
     if constexpr (W == 0 && OP != POP_FOR_AUTO) return;  // macros.rs:52 (FOR_AUTO still reports the statistics)
     const int lane = threadIdx.x & 31;
     const int g = lane >> 3, j = lane & 7;
-    const int q = WL::rank_of_group(g);
+    static_assert(!LINEAR || OP == POP_PLAIN || OP == POP_FOR, "cwida row order: bit-packing and FoR only");
+    const int q = LINEAR ? g : WL::rank_of_group(g);
     const char* ip = in + blk * (size_t(128) * TB) + j * 16;
     char* pk = packed + blk * (size_t(128) * W) + j * 16;
 
@@ -591,12 +599,12 @@ pack_warp_kernel(const char* __restrict__ in, char* __restrict__ packed, size_t 
             const unsigned char* sp = tma_in + j * 16;
             seq_rows<RPG>([&](auto ic) {
                 constexpr int i = decltype(ic)::value;
-                src[i] = to_slice<T>(*reinterpret_cast<const uint4*>(sp + warp_row_offset<T, i>(q)));
+                src[i] = to_slice<T>(*reinterpret_cast<const uint4*>(sp + warp_row_offset<T, i, LINEAR>(q)));
             });
         } else {
             seq_rows<RPG>([&](auto ic) {
                 constexpr int i = warp_visit_row<RPG>(decltype(ic)::value);
-                src[i] = load_slice<T>(ip + warp_row_offset<T, i>(q));
+                src[i] = load_slice<T>(ip + warp_row_offset<T, i, LINEAR>(q));
             });
         }
     }
@@ -697,7 +705,7 @@ pack_warp_kernel(const char* __restrict__ in, char* __restrict__ packed, size_t 
             const bool full = (sh0 + unsigned(RPG * W)) / TB == unsigned(NA);  // d == NA, else d == NA-1
 #pragma unroll
             for (int step = 1; step <= 3; ++step) {
-                const int srcl = WL::group_of_rank(step - 1) * 8 + j;
+                const int srcl = (LINEAR ? step - 1 : WL::group_of_rank(step - 1)) * 8 + j;
 #pragma unroll
                 for (int r = 0; r < NR; ++r) {
                     const R mine = full ? s[NA].r[r] : s[NA - 1].r[r];  // s[d]; includes earlier merges when NA == 1

@@ -129,6 +129,19 @@ FL_API fl_status fl_shutdown(void);
      * n_blocks elements each. */                                                                                   \
     FL_API fl_status fl_block_minmax_##SFX(size_t n_blocks, const T* in, T* mins, T* maxs, void* stream);                  \
     FL_API fl_status fl_host_block_minmax_##SFX(size_t n_blocks, const T* in, T* mins, T* maxs);                           \
+    /* cwida/FastLanes row order.  The reference reorders the rows of the bit-packed layout     \
+     * (FL_ORDER, src/macros.rs:20-24) and says so: "not binary compatible with original FastLanes" (README.md:49-56,    \
+     * src/macros.rs:1-9: "it iterates over the elements respecting the transposed ordering").  These four entry points   \
+     * use the ORIGINAL order instead — row r of a block = values r*LANES .. r*LANES+LANES-1 — for the linear           \
+     * encodings (bit-packing, FoR), same lane bit-streams, same 128*width bytes per block.  PARITY UNPINNED: the        \
+     * reference contains no code, test or vector for that layout; the check is a closed-form oracle written from the  \
+     * description above (oracle/cwida.py).  Device pointers only. */                                                   \
+    FL_API fl_status fl_pack_cwida_##SFX(unsigned width, size_t n_blocks, const T* in, T* packed, void* stream);           \
+    FL_API fl_status fl_unpack_cwida_##SFX(unsigned width, size_t n_blocks, const T* packed, T* out, void* stream);        \
+    FL_API fl_status fl_for_pack_cwida_##SFX(unsigned width, size_t n_blocks, const T* in, T reference, T* packed,         \
+                                      void* stream);                                                                \
+    FL_API fl_status fl_unfor_pack_cwida_##SFX(unsigned width, size_t n_blocks, const T* packed, T reference, T* out,      \
+                                        void* stream);                                                              \
     /* FUSED statistics + FoR::for_pack (src/ffor.rs:24-36): reference = the block's own minimum, found in the same   \
      * pass that packs (the warp holds the whole block).  refs_out: n_blocks references (feed them to                 \
      * fl_unfor_pack_refs); spans_out (nullable): n_blocks values max - min — the block is lossless iff                \

@@ -242,3 +242,28 @@ def test_delta_filter_sorted_column_u64(fl, oracle):
     want, sel = expected_bitmap(ts, lo, hi)
     assert np.array_equal(bitmap.cpu().numpy(), want)
     assert int(counts.sum().item()) == int(sel.sum())
+
+
+@pytest.mark.parametrize("tb", [8, 16, 32, 64])
+def test_cwida_row_order_every_width(fl, tb):
+    """SURVEY.md §8f rank 4 (PARITY UNPINNED, see oracle/cwida.py): pack / unpack / for_pack / unfor_pack in the linear row
+    order of the original FastLanes layout, against the closed-form cwida oracle."""
+    from oracle import cwida
+
+    rng = np.random.default_rng(1400 + tb)
+    n = 5
+    for w in range(tb + 1):
+        values = rand_bytes(rng, n * 128 * tb, tb)
+        ref = int(rand_bytes(rng, tb // 8, tb)[0])
+        p = dev_empty(n * 1024 * w // tb, tb)
+        fl.Cwida.pack(w, to_dev(values), p)
+        want_p = cwida.pack(values, w)
+        assert np.array_equal(to_host(p, tb), want_p), (tb, w, "pack")
+        out = dev_empty(n * 1024, tb)
+        fl.Cwida.unpack(w, p, out)
+        assert np.array_equal(to_host(out, tb), cwida.unpack(want_p, w, n)), (tb, w, "unpack")
+        fl.Cwida.for_pack(w, to_dev(values), ref, p)
+        want_fp = cwida.for_pack(values, ref, w)
+        assert np.array_equal(to_host(p, tb), want_fp), (tb, w, "for_pack")
+        fl.Cwida.unfor_pack(w, p, ref, out)
+        assert np.array_equal(to_host(out, tb), cwida.unfor_pack(want_fp, ref, w, n)), (tb, w, "unfor_pack")

@@ -66,6 +66,8 @@ def main():
             rec("pack", w, 128 * (w + tb), lambda: _lib.fn("fl_pack", tb)(w, n, U, P, sp))
             rec("unfor_pack", w, 128 * (w + tb), lambda: _lib.fn("fl_unfor_pack", tb)(w, n, P, 12345 % (1 << tb), U, sp))
             rec("for_pack", w, 128 * (w + tb), lambda: _lib.fn("fl_for_pack", tb)(w, n, U, 12345 % (1 << tb), P, sp))
+            rec("unpack_cwida", w, 128 * (w + tb), lambda: _lib.fn("fl_unpack_cwida", tb)(w, n, P, U, sp))
+            rec("pack_cwida", w, 128 * (w + tb), lambda: _lib.fn("fl_pack_cwida", tb)(w, n, U, P, sp))
             rec("for_pack_auto", w, 128 * (w + tb) + 2 * (tb // 8),
                 lambda: _lib.fn("fl_for_pack_auto", tb)(w, n, U, base.data_ptr(), base.data_ptr() + n * (tb // 8), P, sp))
             rec("undelta_pack", w, 128 * (w + tb + 1), lambda: _lib.fn("fl_undelta_pack", tb)(w, n, P, B, U, sp))
