@@ -8,7 +8,7 @@ NVFLAGS ?= -std=c++17 -O3 -lineinfo $(ARCH) -Xcompiler -fPIC -Xcompiler -fvisibi
 SRC := fastlanes_b200/csrc
 OBJ := build/obj
 LIB := fastlanes_b200/lib/libfastlanes_b200.so
-TYPES := 8 16 32 64
+TYPES := 64 32 16 8
 PARTS := 0 1 2 3
 HDRS := $(SRC)/fl_device.cuh $(SRC)/fl_kernels.cuh $(SRC)/fl_scan.cuh $(SRC)/fl_scan_bits.h $(SRC)/fl_internal.h include/fastlanes_b200.h
 
