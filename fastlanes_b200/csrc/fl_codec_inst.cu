@@ -138,6 +138,23 @@ static cudaError_t do_pack(const LaunchArgs& a) {
             return cudaGetLastError();
         }
     }
+    if constexpr (sizeof(T) == 1 && (OP == POP_PLAIN || OP == POP_FOR) && W > 0 && W < 8) {
+        // u8 at small W: FLB_U8_PACK=slice|warp selects the row-slice kernel (8 threads per block, no cross-group merge
+        // shuffles) or the warp-block kernel below, for A/B measurement; the default is the measured best per width.
+        static const int mode = [] {
+            const char* e = std::getenv("FLB_U8_PACK");
+            if (e && std::strcmp(e, "slice") == 0) return 1;
+            if (e && std::strcmp(e, "warp") == 0) return 0;
+            return -1;
+        }();
+        // measured (profiles/opbench_u8pack_r01.txt): for_pack is faster row-sliced at every W < 8 (5.8-6.5 -> 6.6-6.8 TB/s),
+        // plain pack only at W = 1 (6.2 -> 6.5)
+        if (mode == 1 || (mode < 0 && (OP == POP_FOR || W < 2))) {
+            pack_kernel<T, W, OP><<<grid_for(a.n_blocks), kThreads, 0, a.stream>>>(
+                static_cast<const char*>(a.in), static_cast<char*>(a.out), a.n_blocks, static_cast<const T*>(a.refs), T(a.ref_scalar));
+            return cudaGetLastError();
+        }
+    }
     const unsigned grid = unsigned((a.n_blocks * 32 + kThreads - 1) / kThreads);  // warp-block layout
     // Every variant stages one block per warp in dynamic shared memory: the original-order op as its swizzled tile,
     // the plain / FoR ops as the landing buffer of the TMA bulk load (+3..7% measured, profiles/kbench_r01_tma_pack_u32.txt).

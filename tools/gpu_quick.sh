@@ -1,4 +1,4 @@
 #!/bin/bash
 mkdir -p gpurun_out
-timeout 900 python -m pytest tests/test_gpu_scan.py tests/test_gpu_parity.py -q -m gpu > gpurun_out/pytest_q.log 2>&1; echo "pytest exit $?"; tail -5 gpurun_out/pytest_q.log
-timeout 600 python tools/opbench.py unpack_cwida,pack_cwida,unpack,pack > gpurun_out/opbench_q.log 2>&1; echo "opbench exit $?"; cat gpurun_out/opbench_q.log
+for m in warp slice; do echo "FLB_U8_PACK=$m"; FLB_U8_PACK=$m timeout 300 python tools/opbench.py pack,for_pack --types 8; done 2>&1 | tee gpurun_out/opbench_u8pack.log
+FLB_U8_PACK=slice timeout 300 python -m pytest tests/test_gpu_parity.py -q -m gpu -k "pack_every_width or for_family" 2>&1 | tail -2
