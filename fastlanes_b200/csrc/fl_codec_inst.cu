@@ -221,9 +221,10 @@ cudaError_t launch_pack<elem_t>(int op, const LaunchArgs& a) {
 // fused decode + predicate kernels (fl_scan.cuh)
 template <class T, int W>
 static cudaError_t do_filter(const LaunchArgs& a) {
-    // blocks per warp: 4 amortises the per-warp set-up while the filter is issue-bound (u32 W=8: 285 -> 208 us); from
-    // W ~ 3T/4 it is HBM-bound and one block per warp keeps more loads in flight (profiles/opbench_scan_r01.txt)
-    constexpr int kNB = (sizeof(T) > 1 && 4 * W >= 3 * Lay<T>::TB) ? 1 : 4;  // u8 stays issue-bound up to W = T
+    // blocks per warp: 4 amortises the per-warp set-up while the filter is issue-bound (u32 W=8: 285 -> 208 us); only the
+    // verbatim width W = T of u16/u32/u64 measured (slightly) faster with one block per warp; u64 W=61 loses 25 % with one
+    // (profiles/opbench_scan_r01.txt)
+    constexpr int kNB = (sizeof(T) > 1 && W == Lay<T>::TB) ? 1 : 4;
     const size_t warps = (a.n_blocks + kNB - 1) / kNB;
     const unsigned grid = unsigned((warps * 32 + kThreads - 1) / kThreads);
     // Direct 128-bit loads, not the TMA bulk load: the filter reads little per block and is ALU-bound below W ~ 3T/4,
