@@ -267,3 +267,15 @@ def test_cwida_row_order_every_width(fl, tb):
         assert np.array_equal(to_host(p, tb), want_fp), (tb, w, "for_pack")
         fl.Cwida.unfor_pack(w, p, ref, out)
         assert np.array_equal(to_host(out, tb), cwida.unfor_pack(want_fp, ref, w, n)), (tb, w, "unfor_pack")
+
+
+def test_example_column_scan():
+    """examples/column_scan.py: encode (fused delta chain, fused statistics + FoR) -> two fused scans -> select -> numpy."""
+    import importlib.util
+    import os
+
+    path = os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "examples", "column_scan.py")
+    spec = importlib.util.spec_from_file_location("column_scan", path)
+    mod = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(mod)
+    assert mod.main(257) == 0
