@@ -185,6 +185,11 @@ def test_for_pack_auto_every_width(fl, oracle, tb):
         fits = (v2.max(1) - v2.min(1)).astype(np.uint64) <= np.uint64(mask(w))
         got = to_host(out, tb).reshape(n, 1024)
         assert np.array_equal(got[fits], v2[fits]), (tb, w, "round trip of the lossless blocks")
+        if w in (0, 5, tb):  # spans are optional
+            refs2 = dev_empty(n, tb)
+            packed2 = dev_empty(n * 1024 * w // tb, tb)
+            fl.FoR.for_pack_auto(w, to_dev(values), refs2, packed2)
+            assert np.array_equal(to_host(refs2, tb), v2.min(1)) and np.array_equal(to_host(packed2, tb), to_host(packed, tb))
 
 
 @pytest.mark.parametrize("tb", [8, 16, 32, 64])
