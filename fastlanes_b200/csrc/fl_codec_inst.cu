@@ -9,6 +9,9 @@
 #include "fl_internal.h"
 #include "fl_kernels.cuh"
 
+#ifndef FLB_U8_FILTER_DEFAULT_SLICE
+#define FLB_U8_FILTER_DEFAULT_SLICE 1  // measured: 550-733 us vs 706-872 (profiles/opbench_scan_r01.txt)
+#endif
 #ifndef FLB_U8_ORIG_DEFAULT_SLICE
 #define FLB_U8_ORIG_DEFAULT_SLICE 1  // measured: 6.5-7.1 TB/s vs 4.6-6.4 (profiles/opbench_u8orig_r01.txt)
 #endif
@@ -221,6 +224,21 @@ cudaError_t launch_pack<elem_t>(int op, const LaunchArgs& a) {
 // fused decode + predicate kernels (fl_scan.cuh)
 template <class T, int W>
 static cudaError_t do_filter(const LaunchArgs& a) {
+    if constexpr (sizeof(T) == 1) {
+        // u8: FLB_U8_FILTER=warp|slice selects the warp-block kernel below or the row-slice kernel (A/B; default = measured best)
+        static const bool slice = [] {
+            const char* e = std::getenv("FLB_U8_FILTER");
+            if (e && std::strcmp(e, "warp") == 0) return false;
+            if (e && std::strcmp(e, "slice") == 0) return true;
+            return FLB_U8_FILTER_DEFAULT_SLICE != 0;
+        }();
+        if (slice) {
+            filter_u8_slice_kernel<W><<<grid_for(a.n_blocks), kThreads, 0, a.stream>>>(
+                static_cast<const char*>(a.in), static_cast<unsigned char*>(a.out), a.counts, a.n_blocks,
+                static_cast<const uint8_t*>(a.refs), uint8_t(a.ref_scalar), uint8_t(a.flo), uint8_t(a.fhi));
+            return cudaGetLastError();
+        }
+    }
     // blocks per warp: 4 amortises the per-warp set-up while the filter is issue-bound (u32 W=8: 285 -> 208 us); only the
     // verbatim width W = T of u16/u32/u64 measured (slightly) faster with one block per warp; u64 W=61 loses 25 % with one
     // (profiles/opbench_scan_r01.txt)

@@ -217,6 +217,63 @@ filter_warp_kernel(const char* __restrict__ packed, unsigned char* __restrict__ 
 }
 
 // ---------------------------------------------------------------------------------------------------
+// u8 filter, ROW-SLICE mapping (8 threads = one block, a warp = 4 blocks; same reasoning as the u8 fused chains in
+// fl_kernels.cuh): a 1 KiB block gives a warp too little work to amortise the per-block set-up and the cross-thread
+// byte assembly of filter_warp_kernel.  Here thread j holds ALL 8 rows of lanes 16j .. 16j+15; for u8 index(r, lane) =
+// r*128 + lane (FL_ORDER[0] = 0), so its 16 predicate bits of row r ARE halfword r*8 + j of the block bitmap: no
+// shuffles, no shared memory, one 16-bit store per row (the 8 threads of a block write 16 contiguous bytes).
+// ---------------------------------------------------------------------------------------------------
+template <int W>
+__global__ void __launch_bounds__(kThreads)
+filter_u8_slice_kernel(const char* __restrict__ packed, unsigned char* __restrict__ bitmap, uint32_t* __restrict__ counts,
+                       size_t n_blocks, const uint8_t* __restrict__ refs, uint8_t ref_scalar, uint8_t lo, uint8_t hi) {
+    using T = uint8_t;
+    using R = uint32_t;
+    const size_t tid = size_t(blockIdx.x) * kThreads + threadIdx.x;
+    const size_t blk_raw = tid / kSlicesPerBlock;
+    const int j = int(tid % kSlicesPerBlock);
+    const bool active = blk_raw < n_blocks;  // whole 8-thread groups are active or not; shuffles below stay inside a group
+    const size_t blk = active ? blk_raw : 0;
+    const FilterPred<T, W> pred(refs ? refs[blk] : ref_scalar, lo, hi);
+    const char* pk = packed + blk * (size_t(128) * W) + j * 16;
+    Slice<T> w[W > 0 ? W : 1];
+    seq_rows<W>([&](auto kc) {
+        constexpr int k = decltype(kc)::value;
+        w[k] = load_slice<T>(pk + k * 128);
+    });
+    uint16_t* bm = reinterpret_cast<uint16_t*>(bitmap + blk * 128) + j;
+    uint32_t cnt = 0;
+    seq_rows<8>([&](auto rc) {
+        constexpr int row = decltype(rc)::value;
+        Slice<T> v;
+        if constexpr (W == 0) v = slice_zero<T>();
+        else if constexpr (W == 8) v = w[row];
+        else {
+            constexpr int curr = (row * W) / 8;
+            constexpr int nxt = (curr + 1 < W) ? curr + 1 : curr;
+            v = extract_row<T, W, row>(w[curr], w[nxt]);
+        }
+        uint32_t bits = 0;
+        if constexpr (FilterPred<T, W>::SWAR_FIELD) {
+            constexpr R H = 0x80808080u;
+#pragma unroll
+            for (int r = 0; r < 4; ++r) bits |= top_bits_u8((v.r[r] + pred.p0) & (pred.p1 - v.r[r]) & H) << (4 * r);
+            bits = (bits ^ pred.invert) & 0xFFFFu;
+        } else {
+            slice_range_bits<T, 0>(bits, v, pred.p0, pred.p1, pred.p2);
+            bits &= ~pred.invert;  // empty range
+        }
+        if (active) bm[row * 8] = uint16_t(bits);
+        cnt += uint32_t(__popc(bits));
+    });
+    if (counts != nullptr) {
+#pragma unroll
+        for (int d = 4; d >= 1; d >>= 1) cnt += __shfl_xor_sync(0xffffffffu, cnt, d);
+        if (active && j == 0) counts[blk] = cnt;
+    }
+}
+
+// ---------------------------------------------------------------------------------------------------
 // Delta scan: bit i of the block's bitmap = lo <= untranspose(undelta_pack(packed, base))[i] <= hi — the range scan
 // over a delta-encoded (sorted ids, timestamps) column, answered in ORIGINAL value order without materialising the
 // decoded block (src/delta.rs:48-63 + src/transpose.rs:18-22 + the caller-side loop of README.md:40-41).
