@@ -479,38 +479,48 @@ def main():
         # ---- the same sweep as a SCAN through host buffers: fl_host_unpack_filter_u32 (fused decode + range
         # predicate).  Only the 128-byte bitmap + count per block cross back over PCIe, so
         # this is the host-buffer call where the offload pays.  Extra key, not part of the headline metric.
-        h_bitmap = fl.pinned_empty(n_blocks * 128, np.uint8)
-        h_counts = fl.pinned_empty(n_blocks, np.uint32)
-        host_filter = _lib.fn("fl_host_unpack_filter", 32)
+        # An extra measurement: a failed pinned allocation on ANY rank (8 ranks x 8.5 GiB of page-locked memory) skips it on
+        # every rank — agreed through a collective, so that no rank waits in a barrier the others never reach.
+        h_bitmap = h_counts = None
+        alloc_failed = 0.0
+        try:
+            h_bitmap = fl.pinned_empty(n_blocks * 128, np.uint8)
+            h_counts = fl.pinned_empty(n_blocks, np.uint32)
+        except (fl.FastLanesError, MemoryError):
+            alloc_failed = 1.0
+        if max_over_ranks(alloc_failed, dist, dev) > 0:
+            e2e["scan_filter"] = {"value": None, "error": "pinned allocation for the bitmap failed on a rank"}
+        else:
+            host_filter = _lib.fn("fl_host_unpack_filter", 32)
 
-        def filter_step():
-            for w in WIDTHS:
-                m = (1 << w) - 1
-                st = host_filter(w, n_blocks, h_packed.ctypes.data, 0, m // 4, m // 2, h_bitmap.ctypes.data, h_counts.ctypes.data)
-                if st != 0:
-                    _lib.check(st)
+            def filter_step():
+                for w in WIDTHS:
+                    m = (1 << w) - 1
+                    st = host_filter(w, n_blocks, h_packed.ctypes.data, 0, m // 4, m // 2, h_bitmap.ctypes.data, h_counts.ctypes.data)
+                    if st != 0:
+                        _lib.check(st)
 
-        for w in (1, 16, 32):
-            _lib.check(host_filter(w, n_blocks, h_packed.ctypes.data, 0, 0, 1, h_bitmap.ctypes.data, h_counts.ctypes.data))
-        barrier()
-        t0 = time.perf_counter()
-        for _ in range(args.e2e_steps):
-            filter_step()
-        torch.cuda.synchronize()
-        f_s = max_over_ranks(time.perf_counter() - t0, dist, dev)
-        # check the last call (W=32, range [m/4, m/2]) against the device-resident values of the first 2^10 blocks
-        launch(32)
-        torch.cuda.synchronize()
-        m32 = (1 << 32) - 1
-        vals = out[: 1 << 20].cpu().numpy().view(np.uint32)
-        want = np.packbits((vals >= np.uint32(m32 // 4)) & (vals <= np.uint32(m32 // 2)), bitorder="little")
-        assert np.array_equal(h_bitmap[: want.size], want), "e2e host filter disagrees with the device unpack"
-        e2e["scan_filter"] = {
-            "value": round(ints_per_step * args.e2e_steps / f_s / 1e9, 2), "unit": "Gint/s scanned",
-            "h2d_bytes_per_step": sum(128 * w for w in WIDTHS) * n_blocks,
-            "d2h_bytes_per_step": len(WIDTHS) * n_blocks * 132,
-            "ms_per_step": round(f_s / args.e2e_steps * 1e3, 1),
-            "api": "fl_host_unpack_filter_u32: range predicate lo<=v<=hi per width, bitmap + counts to pinned host memory"}
+            for w in (1, 16, 32):
+                _lib.check(host_filter(w, n_blocks, h_packed.ctypes.data, 0, 0, 1, h_bitmap.ctypes.data, h_counts.ctypes.data))
+            barrier()
+            t0 = time.perf_counter()
+            for _ in range(args.e2e_steps):
+                filter_step()
+            torch.cuda.synchronize()
+            f_s = max_over_ranks(time.perf_counter() - t0, dist, dev)
+            # check the last call (W=32, range [m/4, m/2]) against the device-resident values of the first 2^10 blocks
+            launch(32)
+            torch.cuda.synchronize()
+            m32 = (1 << 32) - 1
+            vals = out[: 1 << 20].cpu().numpy().view(np.uint32)
+            want = np.packbits((vals >= np.uint32(m32 // 4)) & (vals <= np.uint32(m32 // 2)), bitorder="little")
+            assert np.array_equal(h_bitmap[: want.size], want), "e2e host filter disagrees with the device unpack"
+            e2e["scan_filter"] = {
+                "value": round(ints_per_step * args.e2e_steps / f_s / 1e9, 2), "unit": "Gint/s scanned",
+                "h2d_bytes_per_step": sum(128 * w for w in WIDTHS) * n_blocks,
+                "d2h_bytes_per_step": len(WIDTHS) * n_blocks * 132,
+                "ms_per_step": round(f_s / args.e2e_steps * 1e3, 1),
+                "api": "fl_host_unpack_filter_u32: range predicate lo<=v<=hi per width, bitmap + counts to pinned host memory"}
         del h_packed, h_out, h_bitmap, h_counts
 
     cpu = None
