@@ -119,20 +119,58 @@ class _Arg:
             raise FastLanesError(_lib.FL_ERR_NULL, f"{what}: numpy array or torch CUDA tensor required")
 
 
-def _same_space(*args: _Arg) -> bool:
-    dev = {a.device is not None for a in args}
-    if len(dev) != 1:
+class _Space:
+    """Where a call's buffers live: host (falsy) or ONE CUDA device (truthy, `.index`)."""
+    __slots__ = ("index",)
+
+    def __init__(self, index):
+        self.index = index
+
+    def __bool__(self):
+        return self.index is not None
+
+
+def _same_space(*args: _Arg) -> _Space:
+    """All buffers on the host, or all on the SAME CUDA device (a kernel launched on the current device with another
+    device's pointers is an illegal address without peer access and silent NVLink traffic with it)."""
+    devs = {a.device for a in args}
+    if len({d is not None for d in devs}) != 1:
         raise FastLanesError(_lib.FL_ERR_NULL, "all buffers must be host arrays or all CUDA tensors")
+    if len(devs) != 1:
+        raise FastLanesError(_lib.FL_ERR_NULL, f"all CUDA tensors of one call must live on one device, got {sorted(devs)}")
     tb = {a.tbits for a in args}
     if len(tb) != 1:
         raise FastLanesError(_lib.FL_ERR_LEN, "all buffers must share one element type")
-    return dev.pop()
+    return _Space(devs.pop())
 
 
-def _stream():
-    import torch
+def _join_space(space: _Space, *others: _Arg) -> None:
+    """Buffers of a different element type (indices, bitmaps, counts, offsets) must share the call's memory space."""
+    for a in others:
+        if a.device != space.index:
+            raise FastLanesError(_lib.FL_ERR_NULL, "all buffers must be host arrays or CUDA tensors on one device")
 
-    return ctypes.c_void_p(torch.cuda.current_stream().cuda_stream)
+
+class _Launch:
+    """`with _Launch(space) as stream:` — makes the buffers' device current for the call (the C ABI launches on the
+    current device) and yields torch's current stream OF THAT DEVICE; a no-op (stream None) for host buffers."""
+
+    def __init__(self, space: _Space):
+        self.space, self.guard = space, None
+
+    def __enter__(self):
+        if not self.space:
+            return None
+        import torch
+
+        self.guard = torch.cuda.device(self.space.index)
+        self.guard.__enter__()
+        return ctypes.c_void_p(torch.cuda.current_stream(self.space.index).cuda_stream)
+
+    def __exit__(self, *exc):
+        if self.guard is not None:
+            self.guard.__exit__(*exc)
+        return False
 
 
 def _check_width(width: int, tbits: int):
@@ -152,11 +190,12 @@ def _expect(a: _Arg, n: int, what: str):
         raise FastLanesError(_lib.FL_ERR_LEN, f"{what} buffer must hold {n} elements, got {a.n}")
 
 
-def _call(base, tbits, on_device, *args):
-    name = base if on_device else base.replace("fl_", "fl_host_", 1)
-    if on_device:
-        args = args + (_stream(),)
-    _lib.check(_lib.fn(name, tbits)(*args))
+def _call(base, tbits, space, *args):
+    name = base if space else base.replace("fl_", "fl_host_", 1)
+    with _Launch(space) as stream:
+        if space:
+            args = args + (stream,)
+        _lib.check(_lib.fn(name, tbits)(*args))
 
 
 class BitPacking:
@@ -209,8 +248,7 @@ class BitPacking:
         if g.tbits != 64:
             raise FastLanesError(_lib.FL_ERR_LEN, "global_index must be uint64")
         dev = _same_space(p, o)
-        if (g.device is not None) != dev:
-            raise FastLanesError(_lib.FL_ERR_NULL, "all buffers must be host arrays or all CUDA tensors")
+        _join_space(dev, g)
         _check_width(width, p.tbits)
         per = packed_len(p.tbits, width)
         if per and p.n % per:
@@ -221,8 +259,9 @@ class BitPacking:
             import torch
 
             flag = torch.zeros(1, dtype=torch.int32, device=packed.device)
-            _lib.check(_lib.fn("fl_unpack_gather", p.tbits)(width, n_blocks, p.ptr, g.ptr, g.n, o.ptr,
-                                                            flag.data_ptr(), _stream()))
+            with _Launch(dev) as stream:
+                _lib.check(_lib.fn("fl_unpack_gather", p.tbits)(width, n_blocks, p.ptr, g.ptr, g.n, o.ptr,
+                                                                flag.data_ptr(), stream))
             if int(flag.item()):
                 raise FastLanesError(_lib.FL_ERR_INDEX, "index out of range")
         else:
@@ -249,7 +288,7 @@ class FoR:
             r = _Arg(reference, "reference")
             _same_space(i, r)
             _expect(r, n, "Reference")
-            _call("fl_for_pack_refs", i.tbits, True, width, n, i.ptr, r.ptr, o.ptr)
+            _call("fl_for_pack_refs", i.tbits, dev, width, n, i.ptr, r.ptr, o.ptr)
         else:
             _call("fl_for_pack", i.tbits, dev, width, n, i.ptr, _ref_value(reference, i.tbits), o.ptr)
 
@@ -265,7 +304,7 @@ class FoR:
             r = _Arg(reference, "reference")
             _same_space(o, r)
             _expect(r, n, "Reference")
-            _call("fl_unfor_pack_refs", o.tbits, True, width, n, i.ptr, r.ptr, o.ptr)
+            _call("fl_unfor_pack_refs", o.tbits, dev, width, n, i.ptr, r.ptr, o.ptr)
         else:
             _call("fl_unfor_pack", o.tbits, dev, width, n, i.ptr, _ref_value(reference, o.tbits), o.ptr)
 
@@ -287,7 +326,8 @@ class FoR:
         (CUDA tensors).  `references` (one per block) receives the minima; `spans` (optional) max - min per block:
         block b round-trips losslessly iff spans[b] < 2**width."""
         i, r, o = _Arg(input, "input"), _Arg(references, "references"), _Arg(output, "output")
-        if not _same_space(i, r, o):
+        dev = _same_space(i, r, o)
+        if not dev:
             raise FastLanesError(_lib.FL_ERR_NULL, "for_pack_auto takes CUDA tensors")
         _check_width(width, i.tbits)
         n = _n_blocks_unpacked(i, "Input")
@@ -299,7 +339,8 @@ class FoR:
             _same_space(i, s)
             _expect(s, n, "Spans")
             sptr = s.ptr
-        _lib.check(_lib.fn("fl_for_pack_auto", i.tbits)(width, n, i.ptr, r.ptr, sptr, o.ptr, _stream()))
+        with _Launch(dev) as stream:
+            _lib.check(_lib.fn("fl_for_pack_auto", i.tbits)(width, n, i.ptr, r.ptr, sptr, o.ptr, stream))
 
     @staticmethod
     def choose(mins, maxs, tbits: int):
@@ -406,9 +447,8 @@ class Scan:
         p, b = _Arg(packed, "packed"), _Arg(bitmap, "bitmap")
         if b.tbits != 8:
             raise FastLanesError(_lib.FL_ERR_LEN, "bitmap must be uint8")
-        dev = p.device is not None
-        if (b.device is not None) != dev:
-            raise FastLanesError(_lib.FL_ERR_NULL, "all buffers must be host arrays or all CUDA tensors")
+        dev = _Space(p.device)
+        _join_space(dev, b)
         _check_width(width, p.tbits)
         if b.n % 128:
             raise FastLanesError(_lib.FL_ERR_LEN, "bitmap must hold 128 bytes per block")
@@ -417,8 +457,9 @@ class Scan:
         cptr = None
         if counts is not None:
             c = _Arg(counts, "counts")
-            if c.tbits != 32 or (c.device is not None) != dev:
-                raise FastLanesError(_lib.FL_ERR_LEN, "counts must be uint32 in the same memory space")
+            if c.tbits != 32:
+                raise FastLanesError(_lib.FL_ERR_LEN, "counts must be uint32")
+            _join_space(dev, c)
             _expect(c, n, "Counts")
             cptr = c.ptr
         return p, b, dev, n, cptr
@@ -428,8 +469,8 @@ class Scan:
         """(per-block references pointer or None, scalar reference)."""
         if _is_torch(reference) and reference.dim() > 0:
             r = _Arg(reference, "reference")
-            if r.tbits != p.tbits or r.device is None:
-                raise FastLanesError(_lib.FL_ERR_LEN, "per-block references: a CUDA tensor of the packed element type")
+            if r.tbits != p.tbits or r.device is None or r.device != p.device:
+                raise FastLanesError(_lib.FL_ERR_LEN, "per-block references: a CUDA tensor of the packed element type on the same device")
             _expect(r, n, "Reference")
             return r.ptr, 0
         return None, _ref_value(reference, p.tbits)
@@ -442,7 +483,8 @@ class Scan:
         lo_v, hi_v = _ref_value(lo, p.tbits), _ref_value(hi, p.tbits)
         if dev:
             rptr, rval = Scan._reference_args(reference, p, n)
-            _lib.check(_lib.fn("fl_unpack_filter", p.tbits)(width, n, p.ptr, rptr, rval, lo_v, hi_v, b.ptr, cptr, _stream()))
+            with _Launch(dev) as stream:
+                _lib.check(_lib.fn("fl_unpack_filter", p.tbits)(width, n, p.ptr, rptr, rval, lo_v, hi_v, b.ptr, cptr, stream))
         else:
             _lib.check(_lib.fn("fl_host_unpack_filter", p.tbits)(width, n, p.ptr, _ref_value(reference, p.tbits), lo_v,
                                                                  hi_v, b.ptr, cptr))
@@ -458,7 +500,8 @@ class Scan:
         _expect(bs, n * (1024 // p.tbits), "Base")
         lo_v, hi_v = _ref_value(lo, p.tbits), _ref_value(hi, p.tbits)
         if dev:
-            _lib.check(_lib.fn("fl_undelta_pack_filter", p.tbits)(width, n, p.ptr, bs.ptr, lo_v, hi_v, b.ptr, cptr, _stream()))
+            with _Launch(dev) as stream:
+                _lib.check(_lib.fn("fl_undelta_pack_filter", p.tbits)(width, n, p.ptr, bs.ptr, lo_v, hi_v, b.ptr, cptr, stream))
         else:
             _lib.check(_lib.fn("fl_host_undelta_pack_filter", p.tbits)(width, n, p.ptr, bs.ptr, lo_v, hi_v, b.ptr, cptr))
 
@@ -468,13 +511,15 @@ class Scan:
         `offsets` (uint64/int64 per block) = exclusive prefix sum of the per-block counts."""
         p, b, dev, n, _ = Scan._bitmap_args(width, packed, bitmap, None)
         f, o = _Arg(offsets, "offsets"), _Arg(output, "output")
-        if not dev or f.device is None or o.device is None:
+        if not dev:
             raise FastLanesError(_lib.FL_ERR_NULL, "select takes CUDA tensors")
+        _join_space(dev, f, o)
         if f.tbits != 64 or o.tbits != p.tbits:
             raise FastLanesError(_lib.FL_ERR_LEN, "offsets must be 64-bit, output of the packed element type")
         _expect(f, n, "Offsets")
         rptr, rval = Scan._reference_args(reference, p, n)
-        _lib.check(_lib.fn("fl_unpack_select", p.tbits)(width, n, p.ptr, rptr, rval, b.ptr, f.ptr, o.ptr, _stream()))
+        with _Launch(dev) as stream:
+            _lib.check(_lib.fn("fl_unpack_select", p.tbits)(width, n, p.ptr, rptr, rval, b.ptr, f.ptr, o.ptr, stream))
 
 
 class Cwida:
@@ -486,32 +531,33 @@ class Cwida:
     @staticmethod
     def _io(width, unpacked, packed, what_unpacked, what_packed):
         u, p = _Arg(unpacked, what_unpacked), _Arg(packed, what_packed)
-        if not _same_space(u, p):
+        dev = _same_space(u, p)
+        if not dev:
             raise FastLanesError(_lib.FL_ERR_NULL, "the cwida entry points take CUDA tensors")
         _check_width(width, u.tbits)
         n = _n_blocks_unpacked(u, what_unpacked.capitalize())
         _expect(p, n * packed_len(u.tbits, width), what_packed.capitalize())
-        return u, p, n
+        return u, p, n, dev
 
     @staticmethod
     def pack(width: int, input, output) -> None:
-        u, p, n = Cwida._io(width, input, output, "input", "output")
-        _call("fl_pack_cwida", u.tbits, True, width, n, u.ptr, p.ptr)
+        u, p, n, dev = Cwida._io(width, input, output, "input", "output")
+        _call("fl_pack_cwida", u.tbits, dev, width, n, u.ptr, p.ptr)
 
     @staticmethod
     def unpack(width: int, input, output) -> None:
-        u, p, n = Cwida._io(width, output, input, "output", "input")
-        _call("fl_unpack_cwida", u.tbits, True, width, n, p.ptr, u.ptr)
+        u, p, n, dev = Cwida._io(width, output, input, "output", "input")
+        _call("fl_unpack_cwida", u.tbits, dev, width, n, p.ptr, u.ptr)
 
     @staticmethod
     def for_pack(width: int, input, reference, output) -> None:
-        u, p, n = Cwida._io(width, input, output, "input", "output")
-        _call("fl_for_pack_cwida", u.tbits, True, width, n, u.ptr, _ref_value(reference, u.tbits), p.ptr)
+        u, p, n, dev = Cwida._io(width, input, output, "input", "output")
+        _call("fl_for_pack_cwida", u.tbits, dev, width, n, u.ptr, _ref_value(reference, u.tbits), p.ptr)
 
     @staticmethod
     def unfor_pack(width: int, input, reference, output) -> None:
-        u, p, n = Cwida._io(width, output, input, "output", "input")
-        _call("fl_unfor_pack_cwida", u.tbits, True, width, n, p.ptr, _ref_value(reference, u.tbits), u.ptr)
+        u, p, n, dev = Cwida._io(width, output, input, "output", "input")
+        _call("fl_unfor_pack_cwida", u.tbits, dev, width, n, p.ptr, _ref_value(reference, u.tbits), u.ptr)
 
 
 _lib.lib()  # fail loudly at import time if the CUDA library is missing

@@ -81,8 +81,8 @@ static cudaError_t do_unpack(const LaunchArgs& a) {
     size_t smem = 0;
     if constexpr (OP == UOP_DELTA_ORIG) {  // one block staged per warp
         smem = size_t(kThreads / 32) * 128 * Lay<T>::TB;
-        static const cudaError_t attr = cudaFuncSetAttribute(unpack_warp_kernel<T, W, OP, kTma>, cudaFuncAttributeMaxDynamicSharedMemorySize, int(smem));
-        if (attr != cudaSuccess) return attr;
+        static SmemOptIn opt_in;
+        if (const cudaError_t attr = opt_in.ensure(unpack_warp_kernel<T, W, OP, kTma>, smem); attr != cudaSuccess) return attr;
     }
     unpack_warp_kernel<T, W, OP, kTma><<<grid, kThreads, smem, a.stream>>>(
         static_cast<const char*>(a.in), static_cast<char*>(a.out), a.n_blocks, static_cast<const T*>(a.refs),
@@ -164,8 +164,8 @@ static cudaError_t do_pack(const LaunchArgs& a) {
     // (u8: a 1 KiB block does not amortise the mbarrier round trip — measured slower — so it keeps direct loads.)
     constexpr bool kTma = (OP != POP_ORIG_DELTA) && sizeof(T) >= 2;
     const size_t smem = (kTma || OP == POP_ORIG_DELTA) ? size_t(kThreads / 32) * 128 * Lay<T>::TB + (kTma ? (kThreads / 32) * 8 : 0) : 0;
-    static const cudaError_t attr = cudaFuncSetAttribute(pack_warp_kernel<T, W, OP, kTma>, cudaFuncAttributeMaxDynamicSharedMemorySize, int(smem));
-    if (attr != cudaSuccess) return attr;
+    static SmemOptIn opt_in;
+    if (const cudaError_t attr = opt_in.ensure(pack_warp_kernel<T, W, OP, kTma>, smem); attr != cudaSuccess) return attr;
     pack_warp_kernel<T, W, OP, kTma><<<grid, kThreads, smem, a.stream>>>(
         static_cast<const char*>(a.in), static_cast<char*>(a.out), a.n_blocks, static_cast<const T*>(a.refs),
         T(a.ref_scalar), static_cast<const char*>(a.base), static_cast<T*>(a.refs_out), static_cast<T*>(a.spans_out));
@@ -181,8 +181,8 @@ static cudaError_t do_pack_linear(const LaunchArgs& a) {
     const unsigned grid = unsigned((a.n_blocks * 32 + kThreads - 1) / kThreads);
     constexpr bool kTma = sizeof(T) >= 2;
     const size_t smem = kTma ? size_t(kThreads / 32) * (128 * Lay<T>::TB + 8) : 0;
-    static const cudaError_t attr = cudaFuncSetAttribute(pack_warp_kernel<T, W, OP, kTma, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, int(smem));
-    if (attr != cudaSuccess) return attr;
+    static SmemOptIn opt_in;
+    if (const cudaError_t attr = opt_in.ensure(pack_warp_kernel<T, W, OP, kTma, true>, smem); attr != cudaSuccess) return attr;
     pack_warp_kernel<T, W, OP, kTma, true><<<grid, kThreads, smem, a.stream>>>(
         static_cast<const char*>(a.in), static_cast<char*>(a.out), a.n_blocks, static_cast<const T*>(a.refs),
         T(a.ref_scalar), nullptr, nullptr, nullptr);
@@ -306,12 +306,12 @@ cudaError_t launch_delta<elem_t>(bool undo, const LaunchArgs& a) {
     constexpr bool kTma = sizeof(elem_t) >= 2;  // TMA bulk load of the block (u8: too small to pay, see do_pack)
     const size_t smem = kTma ? size_t(kThreads / 32) * (128 * Lay<elem_t>::TB + 8) : 0;
     if (undo) {
-        static const cudaError_t attr = cudaFuncSetAttribute(delta_warp_kernel<elem_t, true, kTma>, cudaFuncAttributeMaxDynamicSharedMemorySize, int(smem));
-        if (attr != cudaSuccess) return attr;
+        static SmemOptIn opt_in;
+        if (const cudaError_t attr = opt_in.ensure(delta_warp_kernel<elem_t, true, kTma>, smem); attr != cudaSuccess) return attr;
         delta_warp_kernel<elem_t, true, kTma><<<grid, kThreads, smem, a.stream>>>(in, base, out, a.n_blocks);
     } else {
-        static const cudaError_t attr = cudaFuncSetAttribute(delta_warp_kernel<elem_t, false, kTma>, cudaFuncAttributeMaxDynamicSharedMemorySize, int(smem));
-        if (attr != cudaSuccess) return attr;
+        static SmemOptIn opt_in;
+        if (const cudaError_t attr = opt_in.ensure(delta_warp_kernel<elem_t, false, kTma>, smem); attr != cudaSuccess) return attr;
         delta_warp_kernel<elem_t, false, kTma><<<grid, kThreads, smem, a.stream>>>(in, base, out, a.n_blocks);
     }
     return cudaGetLastError();
@@ -321,8 +321,8 @@ template <class T, bool UNDO>
 static cudaError_t do_transpose_warp(const LaunchArgs& a) {
     const unsigned grid = unsigned((a.n_blocks * 32 + kThreads - 1) / kThreads);
     const size_t smem = size_t(kThreads / 32) * 128 * Lay<T>::TB;
-    static const cudaError_t attr = cudaFuncSetAttribute(transpose_warp_kernel<T, UNDO>, cudaFuncAttributeMaxDynamicSharedMemorySize, int(smem));
-    if (attr != cudaSuccess) return attr;
+    static SmemOptIn opt_in;
+    if (const cudaError_t attr = opt_in.ensure(transpose_warp_kernel<T, UNDO>, smem); attr != cudaSuccess) return attr;
     transpose_warp_kernel<T, UNDO><<<grid, kThreads, smem, a.stream>>>(static_cast<const char*>(a.in), static_cast<char*>(a.out), a.n_blocks);
     return cudaGetLastError();
 }

@@ -1,10 +1,29 @@
 // fl_internal.h — internal launch interface between the per-type kernel translation units and the C ABI.
 #pragma once
+#include <atomic>
 #include <cstddef>
 #include <cstdint>
 #include <cuda_runtime.h>
 
 namespace flb {
+
+// Opt-in to more than 48 KiB of dynamic shared memory.  The attribute belongs to the (function, device) pair, so it is
+// cached per device ordinal — one bit per device in a per-call-site mask — and a failure is never cached.
+struct SmemOptIn {
+    std::atomic<uint64_t> done[4] = {};  // 256 device ordinals
+    template <class K>
+    cudaError_t ensure(K kernel, size_t smem) {
+        int dev = 0;
+        cudaError_t e = cudaGetDevice(&dev);
+        if (e != cudaSuccess) return e;
+        const bool cacheable = dev >= 0 && dev < 256;
+        const uint64_t bit = uint64_t(1) << (dev & 63);
+        if (cacheable && (done[dev >> 6].load(std::memory_order_acquire) & bit)) return cudaSuccess;
+        e = cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, int(smem));
+        if (e == cudaSuccess && cacheable) done[dev >> 6].fetch_or(bit, std::memory_order_release);
+        return e;
+    }
+};
 
 struct LaunchArgs {
     const void* in = nullptr;    // unpacked input (pack/delta/transpose) or packed input (unpack family)
