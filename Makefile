@@ -73,3 +73,7 @@ build/test_traits: tests/cpp/test_traits.cpp include/fastlanes_b200.hpp include/
 build/test_scan_bits: tests/cpp/test_scan_bits.cpp $(SRC)/fl_scan_bits.h
 	mkdir -p build
 	g++ -std=c++17 -O1 -Wall -I$(SRC) -o $@ $<
+
+# latency of the single-block drop-in call from compiled host code (tools/latbench.cpp)
+build/latbench: tools/latbench.cpp include/fastlanes_b200.h $(LIB)
+	g++ -std=c++17 -O2 -Iinclude -o $@ $< -Lfastlanes_b200/lib -lfastlanes_b200 -Wl,-rpath,'$$ORIGIN/../fastlanes_b200/lib'

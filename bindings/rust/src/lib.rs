@@ -226,6 +226,96 @@ pub mod scan {
     }
 }
 
+/// Multi-GPU in one process: a context owns one worker thread per device and runs contiguous block shards of every
+/// array of a call on the devices concurrently (`fl_ctx_*`, include/fastlanes_b200.h).  The batched counterpart of the
+/// runtime-width family (`src/bitpacking.rs:109-129` in the reference): whole column chunks, host slices in and out.
+pub mod context {
+    use core::ffi::c_void;
+    #[repr(C)]
+    pub struct FlCtx { _private: [u8; 0] }
+    extern "C" {
+        fn fl_ctx_create(devices: *const i32, n_devices: i32, ctx: *mut *mut FlCtx) -> i32;
+        fn fl_ctx_destroy(ctx: *mut FlCtx) -> i32;
+        fn fl_ctx_device_count(ctx: *const FlCtx) -> i32;
+        fn fl_ctx_block_range(ctx: *const FlCtx, n_blocks: usize, i: i32, first: *mut usize, end: *mut usize) -> i32;
+        fn fl_ctx_host_alloc(ctx: *mut FlCtx, n_blocks: usize, bytes_per_block: usize, p: *mut *mut c_void) -> i32;
+        fn fl_host_free(p: *mut c_void) -> i32;
+        fn fl_ctx_host_unpack_u32(ctx: *mut FlCtx, width: u32, n_blocks: usize, packed: *const u32, out: *mut u32) -> i32;
+        fn fl_ctx_host_pack_u32(ctx: *mut FlCtx, width: u32, n_blocks: usize, input: *const u32, packed: *mut u32) -> i32;
+        fn fl_ctx_host_undelta_pack_u32(ctx: *mut FlCtx, width: u32, n_blocks: usize, packed: *const u32, base: *const u32,
+                                        out: *mut u32) -> i32;
+        fn fl_ctx_host_unpack_filter_u32(ctx: *mut FlCtx, width: u32, n_blocks: usize, packed: *const u32, reference: u32,
+                                         lo: u32, hi: u32, bitmap: *mut u8, counts: *mut u32) -> i32;
+        // ... the same for u8 / u16 / u64 and for for_pack / unfor_pack / delta / undelta / (un)transpose / fused chains
+    }
+
+    pub struct Context { raw: *mut FlCtx }
+    unsafe impl Send for Context {}
+
+    impl Context {
+        /// `devices`: CUDA ordinals; empty = every visible device.
+        pub fn new(devices: &[i32]) -> Self {
+            let mut raw = core::ptr::null_mut();
+            let st = unsafe { fl_ctx_create(if devices.is_empty() { core::ptr::null() } else { devices.as_ptr() }, devices.len() as i32, &mut raw) };
+            super::check(st, "fl_ctx_create");
+            Context { raw }
+        }
+        pub fn devices(&self) -> usize { unsafe { fl_ctx_device_count(self.raw) as usize } }
+        /// Blocks `[first, end)` of an `n_blocks` batch run on shard `i`.
+        pub fn block_range(&self, n_blocks: usize, i: usize) -> (usize, usize) {
+            let (mut a, mut b) = (0usize, 0usize);
+            super::check(unsafe { fl_ctx_block_range(self.raw, n_blocks, i as i32, &mut a, &mut b) }, "fl_ctx_block_range");
+            (a, b)
+        }
+        /// Page-locked `u32` buffer whose pages sit on the NUMA node of the device that will copy them.
+        pub fn pinned_u32(&mut self, n_blocks: usize, elems_per_block: usize) -> PinnedU32 {
+            let mut p = core::ptr::null_mut();
+            super::check(unsafe { fl_ctx_host_alloc(self.raw, n_blocks, elems_per_block * 4, &mut p) }, "fl_ctx_host_alloc");
+            PinnedU32 { ptr: p as *mut u32, len: n_blocks * elems_per_block }
+        }
+        /// Batched `BitPacking::unchecked_unpack` over `output.len() / 1024` blocks, sharded over the devices.
+        pub fn unpack_u32(&mut self, width: usize, packed: &[u32], output: &mut [u32]) {
+            let n = output.len() / 1024;
+            assert_eq!(output.len(), n * 1024, "Output buffer must be a whole number of 1024-element blocks");
+            assert_eq!(packed.len(), n * 32 * width, "Input buffer must be of size n * 1024 * W / T");
+            super::check(unsafe { fl_ctx_host_unpack_u32(self.raw, width as u32, n, packed.as_ptr(), output.as_mut_ptr()) }, "ctx unpack");
+        }
+        pub fn pack_u32(&mut self, width: usize, input: &[u32], packed: &mut [u32]) {
+            let n = input.len() / 1024;
+            assert_eq!(input.len(), n * 1024);
+            assert_eq!(packed.len(), n * 32 * width);
+            super::check(unsafe { fl_ctx_host_pack_u32(self.raw, width as u32, n, input.as_ptr(), packed.as_mut_ptr()) }, "ctx pack");
+        }
+        pub fn undelta_pack_u32(&mut self, width: usize, packed: &[u32], base: &[u32], output: &mut [u32]) {
+            let n = output.len() / 1024;
+            assert_eq!(packed.len(), n * 32 * width);
+            assert_eq!(base.len(), n * 32);
+            super::check(unsafe { fl_ctx_host_undelta_pack_u32(self.raw, width as u32, n, packed.as_ptr(), base.as_ptr(), output.as_mut_ptr()) }, "ctx undelta_pack");
+        }
+        pub fn filter_range_u32(&mut self, width: usize, packed: &[u32], reference: u32, lo: u32, hi: u32, bitmap: &mut [u8], counts: &mut [u32]) {
+            let n = counts.len();
+            assert_eq!(bitmap.len(), n * 128);
+            assert_eq!(packed.len(), n * 32 * width);
+            super::check(unsafe { fl_ctx_host_unpack_filter_u32(self.raw, width as u32, n, packed.as_ptr(), reference, lo, hi, bitmap.as_mut_ptr(), counts.as_mut_ptr()) }, "ctx filter");
+        }
+    }
+    impl Drop for Context {
+        fn drop(&mut self) { unsafe { fl_ctx_destroy(self.raw) }; }
+    }
+
+    pub struct PinnedU32 { ptr: *mut u32, len: usize }
+    impl core::ops::Deref for PinnedU32 {
+        type Target = [u32];
+        fn deref(&self) -> &[u32] { unsafe { core::slice::from_raw_parts(self.ptr, self.len) } }
+    }
+    impl core::ops::DerefMut for PinnedU32 {
+        fn deref_mut(&mut self) -> &mut [u32] { unsafe { core::slice::from_raw_parts_mut(self.ptr, self.len) } }
+    }
+    impl Drop for PinnedU32 {
+        fn drop(&mut self) { unsafe { fl_host_free(self.ptr as *mut c_void) }; }
+    }
+}
+
 #[cfg(test)]
 mod tests {
     //! The reference's own tests, verbatim in spirit (src/bitpacking.rs:249-271, src/lib.rs:71-96).

@@ -29,8 +29,8 @@ from ._lib import FastLanesError, LIB_PATH, exported_symbols  # noqa: F401
 
 FL_ORDER = (0, 4, 2, 6, 1, 5, 3, 7)  # src/lib.rs:22
 
-__all__ = ["BitPacking", "FoR", "Delta", "Transpose", "Scan", "Cwida", "FastLanes", "FastLanesError", "FL_ORDER",
-           "packed_len", "version", "device_count", "init", "host_configure", "pinned_empty", "shutdown"]
+__all__ = ["BitPacking", "FoR", "Delta", "Transpose", "Scan", "Cwida", "Context", "FastLanes", "FastLanesError", "FL_ORDER",
+           "packed_len", "version", "device_count", "init", "host_configure", "pinned_empty", "buffer_node", "shutdown"]
 
 
 class FastLanes:
@@ -69,17 +69,14 @@ def shutdown() -> None:
     _lib.check(_lib.lib().fl_shutdown())
 
 
-def pinned_empty(n: int, dtype) -> np.ndarray:
-    """A page-locked numpy array (fl_host_alloc); keeps the allocation alive for the array's lifetime."""
-    dt = np.dtype(dtype)
-    p = ctypes.c_void_p()
-    _lib.check(_lib.lib().fl_host_alloc(ctypes.byref(p), max(1, n * dt.itemsize)))
-    buf = (ctypes.c_uint8 * (n * dt.itemsize)).from_address(p.value)
+def _pinned_view(ptr: int, n: int, dt) -> np.ndarray:
+    """numpy view of a library-owned page-locked allocation; fl_host_free runs when the last view dies."""
+    buf = (ctypes.c_uint8 * (n * dt.itemsize)).from_address(ptr)
     arr = np.frombuffer(buf, dtype=dt, count=n)
 
     class _Owner:
-        def __init__(self, ptr):
-            self.ptr = ptr
+        def __init__(self, p):
+            self.ptr = p
 
         def __del__(self):
             try:
@@ -87,10 +84,21 @@ def pinned_empty(n: int, dtype) -> np.ndarray:
             except Exception:
                 pass
 
-    owner = _Owner(p.value)
-    # tie the owner to the base buffer so that views keep it alive
-    buf._fl_owner = owner
+    buf._fl_owner = _Owner(ptr)  # tie the owner to the base buffer so that views keep it alive
     return arr
+
+
+def pinned_empty(n: int, dtype) -> np.ndarray:
+    """A page-locked numpy array on the NUMA node of the current CUDA device (fl_host_alloc)."""
+    dt = np.dtype(dtype)
+    p = ctypes.c_void_p()
+    _lib.check(_lib.lib().fl_host_alloc(ctypes.byref(p), max(1, n * dt.itemsize)))
+    return _pinned_view(p.value, n, dt)
+
+
+def buffer_node(a: np.ndarray, byte_offset: int = 0) -> int:
+    """NUMA node holding the page at `byte_offset` of a host array (fl_host_buffer_node), -1 if unknown."""
+    return _lib.lib().fl_host_buffer_node(a.ctypes.data + byte_offset)
 
 
 # ---- argument plumbing ---------------------------------------------------------------------------
@@ -558,6 +566,190 @@ class Cwida:
     def unfor_pack(width: int, input, reference, output) -> None:
         u, p, n, dev = Cwida._io(width, output, input, "output", "input")
         _call("fl_unfor_pack_cwida", u.tbits, dev, width, n, p.ptr, _ref_value(reference, u.tbits), u.ptr)
+
+
+class Context:
+    """`fl_ctx`: one process, several GPUs, contiguous block shards (SURVEY.md §8e behind the C ABI).  Methods mirror the
+    trait calls above for HOST arrays; blocks [n*i/G, n*(i+1)/G) of every array run on device i through that device's
+    own copy pipeline, concurrently.  `devices=None` = all visible devices; a device may be listed more than once."""
+
+    def __init__(self, devices=None):
+        self._h = ctypes.c_void_p()
+        if devices is None:
+            _lib.check(_lib.lib().fl_ctx_create(None, 0, ctypes.byref(self._h)))
+        else:
+            arr = (ctypes.c_int * len(devices))(*devices)
+            _lib.check(_lib.lib().fl_ctx_create(arr, len(devices), ctypes.byref(self._h)))
+
+    def close(self) -> None:
+        if self._h:
+            _lib.lib().fl_ctx_destroy(self._h)
+            self._h = ctypes.c_void_p()
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def __enter__(self):
+        return self
+
+    def __exit__(self, *exc):
+        self.close()
+        return False
+
+    @property
+    def devices(self) -> list:
+        L = _lib.lib()
+        return [L.fl_ctx_device(self._h, i) for i in range(L.fl_ctx_device_count(self._h))]
+
+    def block_range(self, n_blocks: int, i: int) -> tuple:
+        b0, b1 = ctypes.c_size_t(), ctypes.c_size_t()
+        _lib.check(_lib.lib().fl_ctx_block_range(self._h, n_blocks, i, ctypes.byref(b0), ctypes.byref(b1)))
+        return b0.value, b1.value
+
+    def pinned_empty(self, n_blocks: int, elems_per_block: int, dtype) -> np.ndarray:
+        """Page-locked array of n_blocks * elems_per_block elements whose pages follow the shards (fl_ctx_host_alloc)."""
+        dt = np.dtype(dtype)
+        p = ctypes.c_void_p()
+        _lib.check(_lib.lib().fl_ctx_host_alloc(self._h, n_blocks, elems_per_block * dt.itemsize, ctypes.byref(p)))
+        return _pinned_view(p.value, n_blocks * elems_per_block, dt)
+
+    # ---- host arrays, sharded -----------------------------------------------------------------------
+    @staticmethod
+    def _host(*arrays):
+        args = [_Arg(a, "buffer") for a in arrays]
+        if _same_space(*args):
+            raise FastLanesError(_lib.FL_ERR_NULL, "Context methods take host (numpy) arrays")
+        return args
+
+    def _call(self, name, tbits, *args):
+        _lib.check(_lib.fn(name, tbits)(self._h, *args))
+
+    def pack(self, width: int, input, output) -> None:
+        i, o = self._host(input, output)
+        _check_width(width, i.tbits)
+        n = _n_blocks_unpacked(i, "Input")
+        _expect(o, n * packed_len(i.tbits, width), "Output")
+        self._call("fl_ctx_host_pack", i.tbits, width, n, i.ptr, o.ptr)
+
+    def unpack(self, width: int, input, output) -> None:
+        i, o = self._host(input, output)
+        _check_width(width, o.tbits)
+        n = _n_blocks_unpacked(o, "Output")
+        _expect(i, n * packed_len(o.tbits, width), "Input")
+        self._call("fl_ctx_host_unpack", o.tbits, width, n, i.ptr, o.ptr)
+
+    def for_pack(self, width: int, input, reference, output) -> None:
+        i, o = self._host(input, output)
+        _check_width(width, i.tbits)
+        n = _n_blocks_unpacked(i, "Input")
+        _expect(o, n * packed_len(i.tbits, width), "Output")
+        self._call("fl_ctx_host_for_pack", i.tbits, width, n, i.ptr, _ref_value(reference, i.tbits), o.ptr)
+
+    def unfor_pack(self, width: int, input, reference, output) -> None:
+        i, o = self._host(input, output)
+        _check_width(width, o.tbits)
+        n = _n_blocks_unpacked(o, "Output")
+        _expect(i, n * packed_len(o.tbits, width), "Input")
+        self._call("fl_ctx_host_unfor_pack", o.tbits, width, n, i.ptr, _ref_value(reference, o.tbits), o.ptr)
+
+    def _delta3(self, name, input, base, output, width=None, packed_in=True):
+        i, b, o = self._host(input, base, output)
+        unp = o if packed_in else i
+        n = _n_blocks_unpacked(unp, "Unpacked")
+        _expect(b, n * (1024 // unp.tbits), "Base")
+        if width is None:
+            _expect(i, n * 1024, "Input")
+            _expect(o, n * 1024, "Output")
+            self._call(name, unp.tbits, n, i.ptr, b.ptr, o.ptr)
+        else:
+            _check_width(width, unp.tbits)
+            _expect(i if packed_in else o, n * packed_len(unp.tbits, width), "Packed")
+            self._call(name, unp.tbits, width, n, i.ptr, b.ptr, o.ptr)
+
+    def delta(self, input, base, output) -> None:
+        self._delta3("fl_ctx_host_delta", input, base, output)
+
+    def undelta(self, input, base, output) -> None:
+        self._delta3("fl_ctx_host_undelta", input, base, output)
+
+    def undelta_pack(self, width: int, input, base, output) -> None:
+        self._delta3("fl_ctx_host_undelta_pack", input, base, output, width)
+
+    def undelta_pack_untranspose(self, width: int, input, base, output) -> None:
+        self._delta3("fl_ctx_host_undelta_pack_untranspose", input, base, output, width)
+
+    def transpose_delta_pack(self, width: int, input, base, output) -> None:
+        self._delta3("fl_ctx_host_transpose_delta_pack", input, base, output, width, packed_in=False)
+
+    def transpose(self, input, output) -> None:
+        i, o = self._host(input, output)
+        n = _n_blocks_unpacked(i, "Input")
+        _expect(o, n * 1024, "Output")
+        self._call("fl_ctx_host_transpose", i.tbits, n, i.ptr, o.ptr)
+
+    def untranspose(self, input, output) -> None:
+        i, o = self._host(input, output)
+        n = _n_blocks_unpacked(i, "Input")
+        _expect(o, n * 1024, "Output")
+        self._call("fl_ctx_host_untranspose", i.tbits, n, i.ptr, o.ptr)
+
+    def block_minmax(self, input, mins, maxs) -> None:
+        i, lo, hi = self._host(input, mins, maxs)
+        n = _n_blocks_unpacked(i, "Input")
+        _expect(lo, n, "Mins")
+        _expect(hi, n, "Maxs")
+        self._call("fl_ctx_host_block_minmax", i.tbits, n, i.ptr, lo.ptr, hi.ptr)
+
+    def filter_range(self, width: int, packed, reference, lo, hi, bitmap, counts=None) -> None:
+        p, b, dev, n, cptr = Scan._bitmap_args(width, packed, bitmap, counts)
+        if dev:
+            raise FastLanesError(_lib.FL_ERR_NULL, "Context methods take host (numpy) arrays")
+        self._call("fl_ctx_host_unpack_filter", p.tbits, width, n, p.ptr, _ref_value(reference, p.tbits),
+                   _ref_value(lo, p.tbits), _ref_value(hi, p.tbits), b.ptr, cptr)
+
+    def filter_range_delta(self, width: int, packed, base, lo, hi, bitmap, counts=None) -> None:
+        p, b, dev, n, cptr = Scan._bitmap_args(width, packed, bitmap, counts)
+        if dev:
+            raise FastLanesError(_lib.FL_ERR_NULL, "Context methods take host (numpy) arrays")
+        bs = _Arg(base, "base")
+        _same_space(p, bs)
+        _expect(bs, n * (1024 // p.tbits), "Base")
+        self._call("fl_ctx_host_undelta_pack_filter", p.tbits, width, n, p.ptr, bs.ptr, _ref_value(lo, p.tbits),
+                   _ref_value(hi, p.tbits), b.ptr, cptr)
+
+    # ---- device tensors: the trivial block shard / gather (peer copies over NVLink) ------------------
+    def scatter_blocks(self, src, elems_per_block: int, root: int = 0) -> list:
+        """`src`: CUDA tensor on context device `root` holding whole blocks; returns one new tensor per shard, on that
+        shard's device, holding blocks block_range(i) (fl_ctx_scatter_blocks)."""
+        import torch
+
+        n = src.numel() // elems_per_block
+        devs = self.devices
+        shards = []
+        for i, d in enumerate(devs):
+            b0, b1 = self.block_range(n, i)
+            shards.append(torch.empty((b1 - b0) * elems_per_block, dtype=src.dtype, device=f"cuda:{d}"))
+        torch.cuda.synchronize(src.device)
+        ptrs = (ctypes.c_void_p * len(devs))(*[s.data_ptr() if s.numel() else None for s in shards])
+        # empty shards are never dereferenced (their block range is empty)
+        _lib.check(_lib.lib().fl_ctx_scatter_blocks(self._h, elems_per_block * src.element_size(), n, src.data_ptr(), root, ptrs))
+        return shards
+
+    def gather_blocks(self, shards: list, elems_per_block: int, root: int = 0):
+        """Inverse of scatter_blocks: returns one tensor on context device `root` (fl_ctx_gather_blocks)."""
+        import torch
+
+        n = sum(s.numel() for s in shards) // elems_per_block
+        devs = self.devices
+        out = torch.empty(n * elems_per_block, dtype=shards[0].dtype, device=f"cuda:{devs[root]}")
+        for s in shards:
+            torch.cuda.synchronize(s.device)
+        ptrs = (ctypes.c_void_p * len(devs))(*[s.data_ptr() if s.numel() else None for s in shards])
+        _lib.check(_lib.lib().fl_ctx_gather_blocks(self._h, elems_per_block * out.element_size(), n, ptrs, root, out.data_ptr()))
+        return out
 
 
 _lib.lib()  # fail loudly at import time if the CUDA library is missing

@@ -15,7 +15,7 @@ FL_OK, FL_ERR_WIDTH, FL_ERR_LEN, FL_ERR_INDEX, FL_ERR_ALIGN, FL_ERR_CUDA, FL_ERR
 TYPE_SUFFIXES = {8: "u8", 16: "u16", 32: "u32", 64: "u64"}
 _CT = {8: ctypes.c_uint8, 16: ctypes.c_uint16, 32: ctypes.c_uint32, 64: ctypes.c_uint64}
 
-# name -> (argument kinds) ; 'w' width, 'n' size_t, 'p' pointer, 'r' element by value, 's' stream
+# name -> (argument kinds) ; 'w' width, 'n' size_t, 'p' pointer, 'r' element by value, 's' stream, 'c' fl_ctx*
 _PER_TYPE = {
     "fl_pack": "wnpps", "fl_host_pack": "wnpp",
     "fl_unpack": "wnpps", "fl_host_unpack": "wnpp",
@@ -34,9 +34,20 @@ _PER_TYPE = {
     "fl_undelta_pack_filter": "wnpprrpps", "fl_host_undelta_pack_filter": "wnpprrpp",
     "fl_transpose": "npps", "fl_untranspose": "npps",
     "fl_host_transpose": "npp", "fl_host_untranspose": "npp",
+    # context family (multi-device, block-sharded): fl_host_<op> with a leading fl_ctx*
+    "fl_ctx_host_pack": "cwnpp", "fl_ctx_host_unpack": "cwnpp",
+    "fl_ctx_host_for_pack": "cwnprp", "fl_ctx_host_unfor_pack": "cwnprp",
+    "fl_ctx_host_delta": "cnppp", "fl_ctx_host_undelta": "cnppp",
+    "fl_ctx_host_undelta_pack": "cwnppp", "fl_ctx_host_undelta_pack_untranspose": "cwnppp",
+    "fl_ctx_host_transpose_delta_pack": "cwnppp",
+    "fl_ctx_host_transpose": "cnpp", "fl_ctx_host_untranspose": "cnpp",
+    "fl_ctx_host_block_minmax": "cnppp",
+    "fl_ctx_host_unpack_filter": "cwnprrrpp", "fl_ctx_host_undelta_pack_filter": "cwnpprrpp",
 }
 _GLOBAL = ["fl_version", "fl_last_error_string", "fl_status_string", "fl_device_count", "fl_device_numa_node", "fl_init", "fl_host_configure",
-           "fl_host_alloc", "fl_host_free", "fl_host_register", "fl_host_unregister", "fl_shutdown"]
+           "fl_host_alloc", "fl_host_free", "fl_host_buffer_node", "fl_host_register", "fl_host_unregister", "fl_host_copy_probe",
+           "fl_shutdown", "fl_ctx_create", "fl_ctx_destroy", "fl_ctx_device_count", "fl_ctx_device", "fl_ctx_block_range",
+           "fl_ctx_host_alloc", "fl_ctx_host_copy_probe", "fl_ctx_scatter_blocks", "fl_ctx_gather_blocks"]
 
 
 def exported_symbols() -> list[str]:
@@ -80,12 +91,30 @@ def lib() -> ctypes.CDLL:
     L.fl_host_free.argtypes = [ctypes.c_void_p]
     L.fl_host_register.argtypes = [ctypes.c_void_p, ctypes.c_size_t]
     L.fl_host_unregister.argtypes = [ctypes.c_void_p]
+    L.fl_host_buffer_node.restype = ctypes.c_int
+    L.fl_host_buffer_node.argtypes = [ctypes.c_void_p]
+    L.fl_host_copy_probe.argtypes = [ctypes.c_size_t, ctypes.c_size_t, ctypes.c_size_t, ctypes.c_void_p, ctypes.c_void_p]
+    L.fl_ctx_create.argtypes = [ctypes.POINTER(ctypes.c_int), ctypes.c_int, ctypes.POINTER(ctypes.c_void_p)]
+    L.fl_ctx_destroy.argtypes = [ctypes.c_void_p]
+    L.fl_ctx_device_count.restype = ctypes.c_int
+    L.fl_ctx_device_count.argtypes = [ctypes.c_void_p]
+    L.fl_ctx_device.restype = ctypes.c_int
+    L.fl_ctx_device.argtypes = [ctypes.c_void_p, ctypes.c_int]
+    L.fl_ctx_block_range.argtypes = [ctypes.c_void_p, ctypes.c_size_t, ctypes.c_int, ctypes.POINTER(ctypes.c_size_t),
+                                     ctypes.POINTER(ctypes.c_size_t)]
+    L.fl_ctx_host_alloc.argtypes = [ctypes.c_void_p, ctypes.c_size_t, ctypes.c_size_t, ctypes.POINTER(ctypes.c_void_p)]
+    L.fl_ctx_host_copy_probe.argtypes = [ctypes.c_void_p, ctypes.c_size_t, ctypes.c_size_t, ctypes.c_size_t, ctypes.c_void_p,
+                                         ctypes.c_void_p]
+    L.fl_ctx_scatter_blocks.argtypes = [ctypes.c_void_p, ctypes.c_size_t, ctypes.c_size_t, ctypes.c_void_p, ctypes.c_int,
+                                        ctypes.POINTER(ctypes.c_void_p)]
+    L.fl_ctx_gather_blocks.argtypes = [ctypes.c_void_p, ctypes.c_size_t, ctypes.c_size_t, ctypes.POINTER(ctypes.c_void_p),
+                                       ctypes.c_int, ctypes.c_void_p]
     for base, kinds in _PER_TYPE.items():
         for tb, sfx in TYPE_SUFFIXES.items():
             fn = getattr(L, f"{base}_{sfx}")
             fn.restype = ctypes.c_int
             fn.argtypes = [{"w": ctypes.c_uint, "n": ctypes.c_size_t, "p": ctypes.c_void_p, "r": _CT[tb],
-                            "s": ctypes.c_void_p}[k] for k in kinds]
+                            "s": ctypes.c_void_p, "c": ctypes.c_void_p}[k] for k in kinds]
     _lib = L
     return L
 

@@ -256,7 +256,13 @@ static cudaError_t do_filter(const LaunchArgs& a) {
 template <class T, int W>
 static cudaError_t do_select(const LaunchArgs& a) {
     const unsigned grid = unsigned((a.n_blocks * 32 + kThreads - 1) / kThreads);
-    select_warp_kernel<T, W, (sizeof(T) >= 2)><<<grid, kThreads, 0, a.stream>>>(
+    // per-warp staging buffer of the compacted values (fl_scan.cuh); u64: 64 KiB per CTA, so the packed block is read
+    // with direct loads there instead of adding the TMA landing buffer on top
+    constexpr bool kTma = sizeof(T) == 2 || sizeof(T) == 4;
+    const size_t smem = size_t(kThreads / 32) * select_stage_bytes<T>();
+    static SmemOptIn opt_in;
+    if (const cudaError_t attr = opt_in.ensure(select_warp_kernel<T, W, kTma>, smem); attr != cudaSuccess) return attr;
+    select_warp_kernel<T, W, kTma><<<grid, kThreads, smem, a.stream>>>(
         static_cast<const char*>(a.in), static_cast<const unsigned char*>(a.bitmap), a.offsets, static_cast<T*>(a.out),
         a.n_blocks, static_cast<const T*>(a.refs), T(a.ref_scalar));
     return cudaGetLastError();

@@ -365,18 +365,18 @@ __device__ __forceinline__ T slice_lane(const Slice<T>& s, int k) {
     else return T(s.r[k >> 2] >> (8 * (k & 3)));
 }
 
-// predicated store: *p = v iff b != 0, as ONE predicated st.global (no branch around the store)
+// ---------------------------------------------------------------------------------------------------
+// select (dense compaction of the values a bitmap selects).  Store side, round 2: the round-1 kernel issued one
+// predicated 1-element st.global per value straight from the decode registers — 1024 scattered stores per block whose
+// partial-sector writes cost 3.0x the algorithmic L2 write traffic (profiles/ncu_s2_r01.md).  Now the selected values
+// are first compacted into a warp-private shared-memory staging buffer (predicated STS at the value's rank, computed
+// as before from the per-word popcount scan), laid out with the SAME 16-byte phase as the destination out + offsets[b],
+// and then drained with full 16-byte coalesced STG.128 — only the (at most two) edge vectors of a block's output run
+// use element stores.  Every output byte is written exactly once, in sector-sized pieces.
+//   dynamic shared memory: kThreads/32 warps x select_stage_bytes<T>()
+// ---------------------------------------------------------------------------------------------------
 template <class T>
-__device__ __forceinline__ void st_if(T* p, T v, uint32_t b) {
-    if constexpr (sizeof(T) == 8)
-        asm volatile("{\n .reg .pred q;\n setp.ne.u32 q, %2, 0;\n @q st.global.u64 [%0], %1;\n}" ::"l"(p), "l"(v), "r"(b) : "memory");
-    else if constexpr (sizeof(T) == 4)
-        asm volatile("{\n .reg .pred q;\n setp.ne.u32 q, %2, 0;\n @q st.global.u32 [%0], %1;\n}" ::"l"(p), "r"(v), "r"(b) : "memory");
-    else if constexpr (sizeof(T) == 2)
-        asm volatile("{\n .reg .pred q;\n setp.ne.u32 q, %2, 0;\n @q st.global.u16 [%0], %1;\n}" ::"l"(p), "h"(v), "r"(b) : "memory");
-    else
-        asm volatile("{\n .reg .pred q;\n setp.ne.u32 q, %2, 0;\n @q st.global.u8 [%0], %1;\n}" ::"l"(p), "r"(uint32_t(v)), "r"(b) : "memory");
-}
+__host__ __device__ constexpr int select_stage_bytes() { return 1024 * int(sizeof(T)) + 16; }
 
 template <class T, int W, bool TMA>
 __global__ void __launch_bounds__(kThreads)
@@ -387,6 +387,7 @@ select_warp_kernel(const char* __restrict__ packed, const unsigned char* __restr
     constexpr int TB = Lay<T>::TB;
     constexpr int RPG = WL::RPG;
     constexpr int BPT = 128 / TB;
+    constexpr int EPV = 16 / int(sizeof(T));  // elements per 16-byte vector
     const size_t blk = (size_t(blockIdx.x) * kThreads + threadIdx.x) >> 5;
     if (blk >= n_blocks) return;  // warp-uniform
     const int lane = threadIdx.x & 31;
@@ -404,7 +405,8 @@ select_warp_kernel(const char* __restrict__ packed, const unsigned char* __restr
         const uint32_t t = __shfl_up_sync(0xffffffffu, incl, d);
         if (lane >= d) incl += t;
     }
-    if (__shfl_sync(0xffffffffu, incl, 31) == 0) return;  // nothing selected in this block: skip the decode
+    const uint32_t total = __shfl_sync(0xffffffffu, incl, 31);
+    if (total == 0) return;  // nothing selected in this block: skip the decode
     __shared__ uint2 sel_tile[kThreads / 32][32];  // (bitmap word, exclusive prefix)
     uint2* tile = sel_tile[threadIdx.x >> 5];
     tile[lane] = make_uint2(mword, incl - cnt);
@@ -413,22 +415,52 @@ select_warp_kernel(const char* __restrict__ packed, const unsigned char* __restr
     Slice<T> v[RPG];
     warp_decode_tile<T, W, TMA, (kThreads / 32) * 256>(packed + blk * (size_t(128) * W), lane, q, j, v);
     const Slice<T> rs = slice_splat<T>(ref);
+
+    extern __shared__ __align__(16) unsigned char select_stage_smem[];
     T* o = out + obase;
-    asm volatile("" : "+l"(o));  // keep the block's output base as ONE 64-bit register: stores address it as o + 32-bit rank
+    const uint32_t mis = uint32_t((reinterpret_cast<uintptr_t>(o) & 15u) / sizeof(T));  // phase of the run inside a 16-byte vector
+    T* stage = reinterpret_cast<T*>(select_stage_smem + (threadIdx.x >> 5) * select_stage_bytes<T>()) + mis;
+    // Original index of this thread's first lane in local row i: index(q*RPG + i, j*BPT) (macros.rs:20-24).  Rows of one
+    // 8-row band share FL_ORDER[r/8], so inside a band bit0 = c0 + (r%8)*128: the bit position inside the 32-bit bitmap
+    // word (sh) and the mask of the lower bits are per-thread constants, the word index advances by 4 per row.
+    constexpr int BANDS = RPG > 8 ? RPG / 8 : 1;
+    int c0[BANDS];
+#pragma unroll
+    for (int bnd = 0; bnd < BANDS; ++bnd) {
+        const int r0 = q * RPG + bnd * 8;  // first global row of the band (RPG < 8: of the run)
+        c0[bnd] = scan_fl_order(r0 >> 3) * 16 + (r0 & 7) * 128 + j * BPT;
+    }
 #pragma unroll
     for (int i = 0; i < RPG; ++i) {
-        const int bit0 = row_bitmap_byte(q * RPG + i) * 8 + j * BPT;  // original index of this thread's first lane in row i
+        const int bit0 = c0[i / 8] + (i % 8) * 128;
         const uint2 e = tile[bit0 >> 5];
-        const int sh = bit0 & 31;
+        const int sh = c0[i / 8] & 31;
         const uint32_t bits = (e.x >> sh) & ((BPT == 32) ? 0xffffffffu : ((1u << BPT) - 1u));
         if (bits == 0) continue;  // nothing selected in this thread's slice of the row
-        uint32_t pos = e.y + uint32_t(__popc(e.x & ((1u << sh) - 1u)));  // rank of the slice's first selected value
+        T* sp = stage + (e.y + uint32_t(__popc(e.x & ((1u << sh) - 1u))));  // rank of the slice's first selected value
         const Slice<T> val = slice_add<T>(v[i], rs);  // ffor.rs:47
 #pragma unroll
         for (int k = 0; k < BPT; ++k) {
-            const uint32_t b = (bits >> k) & 1u;
-            st_if<T>(o + pos, slice_lane<T>(val, k), b);
-            pos += b;
+            if (bits & (1u << k)) {  // predicated STS + predicated pointer bump
+                *sp = slice_lane<T>(val, k);
+                ++sp;
+            }
+        }
+    }
+    __syncwarp();
+    // drain: stage[-mis .. ) and o - mis are both 16-byte aligned; vector x covers run elements [x*EPV - mis, ...)
+    const T* sbase = stage - mis;
+    T* gbase = o - mis;
+    const uint32_t end = mis + total;
+    const uint32_t nvec = (end + EPV - 1) / EPV;
+    for (uint32_t x = lane; x < nvec; x += 32) {
+        const uint32_t lo = x * EPV;
+        if (lo >= mis && lo + EPV <= end) {
+            stg128_stream(gbase + lo, *reinterpret_cast<const uint4*>(sbase + lo));
+        } else {
+#pragma unroll
+            for (int e = 0; e < EPV; ++e)
+                if (lo + e >= mis && lo + e < end) gbase[lo + e] = sbase[lo + e];
         }
     }
 }

@@ -60,20 +60,59 @@ FL_API int fl_device_count(void);                    /* 0 when no usable CUDA de
 /* Optional: make `device` current for the calling thread and create its host-path context (streams) up front so the
  * first fl_host_* call does not pay for it.  Every entry point also works without it (contexts are created lazily). */
 FL_API fl_status fl_init(int device);
-/* Host-path tuning for the CURRENT device: blocks per pipelined chunk (0 = default 16384) and
- * number of internal streams (0 = default 3).  Takes effect on the next fl_host_* call. */
+/* Host-path tuning, PROCESS-WIDE (every device, every thread): blocks per pipelined chunk (0 = default 16384, clamped to
+ * the 2^31-block launch limit) and number of internal streams per pipeline (0 = default 3, at most 16).  Takes effect
+ * on the next fl_host_* call. */
 FL_API fl_status fl_host_configure(size_t chunk_blocks, int n_streams);
-/* Page-locked host memory helpers (cudaHostAlloc / cudaHostRegister).  fl_host_alloc places the pages on the NUMA
- * node of the CURRENT device (it runs the allocation on a CPU of that node; FLB_NUMA=0 disables): a D2H stream that
- * crosses the socket interconnect is slower, and the host family is PCIe-bound.  fl_device_numa_node: that node, or
- * -1 when the platform does not say — bind the threads that produce / consume the buffers to it as well. */
+/* Page-locked host memory.  The host family is PCIe-bound and a GPU's DMA runs at full speed only against the memory
+ * of its own socket, so fl_host_alloc places the pages on the NUMA node of the CURRENT device: node lookup =
+ * FLB_NUMA_MAP="n0,n1,.." (per device ordinal) > cudaDevAttrHostNumaId > /sys/bus/pci/devices/<id>/numa_node; placement =
+ * mmap + mbind(MPOL_PREFERRED) + cudaHostRegister (independent of the CPUs the caller is allowed to run on).  When the
+ * node is unknown or the kernel refuses, it is a plain cudaHostAlloc.  FLB_NUMA=0 disables.  fl_host_free releases
+ * either kind.  fl_device_numa_node: the node found for `device`, or -1.  fl_host_buffer_node: the node that actually
+ * holds the page at p (move_pages query), or -1 — to verify a placement. */
 FL_API int fl_device_numa_node(int device);
 FL_API fl_status fl_host_alloc(void** p, size_t bytes);
 FL_API fl_status fl_host_free(void* p);
+FL_API int fl_host_buffer_node(const void* p);
 FL_API fl_status fl_host_register(void* p, size_t bytes);
 FL_API fl_status fl_host_unregister(void* p);
+/* The copies of a host call WITHOUT its kernel, through the same chunked multi-stream pipeline: in_bytes_per_block go
+ * host->device, out_bytes_per_block come back (contents unspecified).  The time of this call is the PCIe ceiling of the
+ * fl_host_* call with the same byte counts on this box (bench.py: e2e.link_ceiling). */
+FL_API fl_status fl_host_copy_probe(size_t in_bytes_per_block, size_t out_bytes_per_block, size_t n_blocks, const void* in,
+                                    void* out);
 /* Release the internal streams and staging buffers of every device used by fl_host_* calls. */
 FL_API fl_status fl_shutdown(void);
+
+/* Multi-device context ------------------------------------------------------------------------------
+ * every op reads and writes exactly one 1024-value block, so a batch shards by contiguous block ranges
+ * with no exchange between devices.  A context owns one worker thread per listed device; fl_ctx_host_<op>_<T> has the
+ * signature of fl_host_<op>_<T> plus the context and runs blocks [n*i/G, n*(i+1)/G) of EVERY array of the call (packed,
+ * unpacked, base, bitmap, counts shard on the same block index) on device i through that device's own host pipeline:
+ * G PCIe links and copy pipelines in one call from one host thread.  The seam it extends is the batched runtime-width
+ * family, src/bitpacking.rs:109-129.  devices == NULL or n_devices <= 0: all visible devices.  A device may be listed
+ * more than once (each entry is an independent shard worker).  Calls on one context are serialised; use one context
+ * per caller thread for concurrency.  No collective library is involved (FL_ERR_NCCL of SURVEY.md §8b does not exist):
+ * the only inter-device traffic is the optional scatter/gather below, plain peer copies over NVLink. */
+typedef struct fl_ctx fl_ctx;
+FL_API fl_status fl_ctx_create(const int* devices, int n_devices, fl_ctx** ctx);
+FL_API fl_status fl_ctx_destroy(fl_ctx* ctx);
+FL_API int fl_ctx_device_count(const fl_ctx* ctx);
+FL_API int fl_ctx_device(const fl_ctx* ctx, int i);         /* CUDA ordinal of shard i, -1 if out of range */
+/* shard i owns blocks [*first, *end) of an n_blocks batch */
+FL_API fl_status fl_ctx_block_range(const fl_ctx* ctx, size_t n_blocks, int i, size_t* first, size_t* end);
+/* Page-locked buffer of n_blocks * bytes_per_block bytes whose pages follow the shards: the byte range of shard i is
+ * placed on the NUMA node of device i (see fl_host_alloc).  Free with fl_host_free. */
+FL_API fl_status fl_ctx_host_alloc(fl_ctx* ctx, size_t n_blocks, size_t bytes_per_block, void** p);
+FL_API fl_status fl_ctx_host_copy_probe(fl_ctx* ctx, size_t in_bytes_per_block, size_t out_bytes_per_block, size_t n_blocks,
+                                        const void* in, void* out);
+/* The "trivial block shard / gather" between DEVICE buffers: `src` / `dst` holds all n_blocks on context device `root`,
+ * shards[i] (device memory of context device i) holds that shard's blocks.  Synchronous peer copies, outside any decode. */
+FL_API fl_status fl_ctx_scatter_blocks(fl_ctx* ctx, size_t bytes_per_block, size_t n_blocks, const void* src, int root,
+                                       void* const* shards);
+FL_API fl_status fl_ctx_gather_blocks(fl_ctx* ctx, size_t bytes_per_block, size_t n_blocks, const void* const* shards, int root,
+                                      void* dst);
 
 /* Per-type entry points ------------------------------------------------------------------------ */
 #define FL_DECLARE_TYPE(SFX, T)                                                                                     \
@@ -175,7 +214,30 @@ FL_API fl_status fl_shutdown(void);
     FL_API fl_status fl_transpose_##SFX(size_t n_blocks, const T* in, T* out, void* stream);                               \
     FL_API fl_status fl_untranspose_##SFX(size_t n_blocks, const T* in, T* out, void* stream);                             \
     FL_API fl_status fl_host_transpose_##SFX(size_t n_blocks, const T* in, T* out);                                        \
-    FL_API fl_status fl_host_untranspose_##SFX(size_t n_blocks, const T* in, T* out);
+    FL_API fl_status fl_host_untranspose_##SFX(size_t n_blocks, const T* in, T* out);                                      \
+    /* Context family: fl_host_<op>_<T> block-sharded over the devices of a context (see fl_ctx above). */          \
+    FL_API fl_status fl_ctx_host_pack_##SFX(fl_ctx* ctx, unsigned width, size_t n_blocks, const T* in, T* packed);         \
+    FL_API fl_status fl_ctx_host_unpack_##SFX(fl_ctx* ctx, unsigned width, size_t n_blocks, const T* packed, T* out);      \
+    FL_API fl_status fl_ctx_host_for_pack_##SFX(fl_ctx* ctx, unsigned width, size_t n_blocks, const T* in, T reference,    \
+                                                T* packed);                                                         \
+    FL_API fl_status fl_ctx_host_unfor_pack_##SFX(fl_ctx* ctx, unsigned width, size_t n_blocks, const T* packed,           \
+                                                  T reference, T* out);                                             \
+    FL_API fl_status fl_ctx_host_delta_##SFX(fl_ctx* ctx, size_t n_blocks, const T* in, const T* base, T* out);            \
+    FL_API fl_status fl_ctx_host_undelta_##SFX(fl_ctx* ctx, size_t n_blocks, const T* in, const T* base, T* out);          \
+    FL_API fl_status fl_ctx_host_undelta_pack_##SFX(fl_ctx* ctx, unsigned width, size_t n_blocks, const T* packed,         \
+                                                    const T* base, T* out);                                         \
+    FL_API fl_status fl_ctx_host_undelta_pack_untranspose_##SFX(fl_ctx* ctx, unsigned width, size_t n_blocks,              \
+                                                                const T* packed, const T* base, T* out);            \
+    FL_API fl_status fl_ctx_host_transpose_delta_pack_##SFX(fl_ctx* ctx, unsigned width, size_t n_blocks, const T* in,     \
+                                                            const T* base, T* packed);                              \
+    FL_API fl_status fl_ctx_host_transpose_##SFX(fl_ctx* ctx, size_t n_blocks, const T* in, T* out);                       \
+    FL_API fl_status fl_ctx_host_untranspose_##SFX(fl_ctx* ctx, size_t n_blocks, const T* in, T* out);                     \
+    FL_API fl_status fl_ctx_host_block_minmax_##SFX(fl_ctx* ctx, size_t n_blocks, const T* in, T* mins, T* maxs);          \
+    FL_API fl_status fl_ctx_host_unpack_filter_##SFX(fl_ctx* ctx, unsigned width, size_t n_blocks, const T* packed,        \
+                                                     T reference, T lo, T hi, uint8_t* bitmap, uint32_t* counts);   \
+    FL_API fl_status fl_ctx_host_undelta_pack_filter_##SFX(fl_ctx* ctx, unsigned width, size_t n_blocks, const T* packed,  \
+                                                           const T* base, T lo, T hi, uint8_t* bitmap,              \
+                                                           uint32_t* counts);
 
 FL_DECLARE_TYPE(u8, uint8_t)
 FL_DECLARE_TYPE(u16, uint16_t)

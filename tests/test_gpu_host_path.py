@@ -147,3 +147,71 @@ def test_pinned_buffers(fl, oracle):
     out = fl.pinned_empty(n * 1024, np.uint32)
     fl.BitPacking.unpack(w, packed, out)
     assert np.array_equal(out, oracle.unpack(np.array(packed), w, threads=4))
+
+
+def test_small_calls_every_op_and_size_boundary(fl, oracle):
+    """The low-latency path (zero-copy page-locked staging, one launch) takes calls whose in + base + out fit in 256 KiB;
+    the block counts here straddle that limit for every type so both paths are compared with the oracle."""
+    rng = np.random.default_rng(21)
+    for tb in (8, 16, 32, 64):
+        per_block = 128 * tb * 2 + 128  # roughly in + out + base bytes at W = T
+        edge = (256 << 10) // per_block
+        for n in (1, 2, edge - 1, edge, edge + 1, 2 * edge + 3):
+            for w in (0, 1, tb // 2 + 1, tb):
+                values = rand_bytes(rng, n * 128 * tb, tb)
+                base = rand_bytes(rng, n * 128, tb)
+                packed = np.zeros(n * 1024 * w // tb, dtype=DT[tb])
+                fl.BitPacking.pack(w, values, packed)
+                assert np.array_equal(packed, oracle.pack(values, w)), (tb, n, w)
+                out = np.full(n * 1024, 0x5A, dtype=DT[tb])
+                fl.Delta.undelta_pack(w, packed, base, out)
+                assert np.array_equal(out, oracle.undelta_pack(packed, base, w, n_blocks=n)), (tb, n, w)
+                fl.Delta.undelta_pack_untranspose(w, packed, base, out)
+                assert np.array_equal(out, oracle.untranspose(oracle.undelta_pack(packed, base, w, n_blocks=n))), (tb, n, w)
+            values = rand_bytes(rng, n * 128 * tb, tb)
+            out = np.zeros_like(values)
+            fl.Transpose.transpose(values, out)
+            assert np.array_equal(out, oracle.transpose(values)), (tb, n)
+
+
+def test_gather_moves_only_referenced_blocks(fl, oracle):
+    """fl_host_unpack_gather: few indices into a large column (zero-copy path), many indices (compacted distinct blocks
+    through device staging), more indices than blocks (whole-column copy), out-of-range index."""
+    rng = np.random.default_rng(22)
+    for tb, w, n_blocks in ((16, 9, 5000), (32, 17, 3000), (64, 33, 700), (8, 5, 4000)):
+        packed = rand_bytes(rng, n_blocks * 128 * w, tb)
+        for n in (1, 7, 130, 2500, n_blocks + 17):
+            gi = rng.integers(0, n_blocks * 1024, size=n, dtype=np.uint64)
+            if n >= 130:  # runs of consecutive blocks and repeated blocks
+                gi[: n // 2] = np.sort(gi[: n // 2])
+                gi[n // 2: n // 2 + 20] = gi[0]
+            out = np.zeros(n, dtype=DT[tb])
+            fl.BitPacking.unpack_gather(w, packed, gi, out)
+            assert np.array_equal(out, oracle.unpack_gather(packed, w, gi)), (tb, w, n)
+        gi = np.array([5, n_blocks * 1024], dtype=np.uint64)
+        with pytest.raises(fl.FastLanesError) as e:
+            fl.BitPacking.unpack_gather(w, packed, gi, np.zeros(2, dtype=DT[tb]))
+        assert e.value.status == 3
+    # the reference's own loop: 1024 unpack_single calls on one block (src/bitpacking.rs:259-271)
+    values = np.arange(1024, dtype=np.uint32)
+    packed = np.zeros(512, dtype=np.uint32)
+    fl.BitPacking.pack(16, values, packed)
+    assert [int(fl.BitPacking.unpack_single(16, packed, i)) for i in range(1024)] == list(range(1024))
+
+
+def test_copy_probe_and_placement_queries(fl):
+    from fastlanes_b200 import _lib
+
+    n = 3000
+    src = fl.pinned_empty(n * 32 * 8, np.uint32)
+    dst = fl.pinned_empty(n * 1024, np.uint32)
+    src.fill(1)
+    assert _lib.lib().fl_host_copy_probe(128 * 8, 4096, n, src.ctypes.data, dst.ctypes.data) == 0
+    assert _lib.lib().fl_host_copy_probe(0, 4096, n, None, dst.ctypes.data) == 0
+    node = _lib.lib().fl_device_numa_node(0)
+    got = fl.buffer_node(dst)
+    assert got >= -1
+    if node >= 0 and got >= 0 and got != node:  # MPOL_PREFERRED is a preference: a full node may spill
+        import warnings
+
+        warnings.warn(f"fl_host_alloc placed the buffer on node {got}, device 0 is on node {node}")

@@ -22,7 +22,7 @@ def test_library_exports_every_declared_symbol():
 
     L = ctypes.CDLL(_lib.LIB_PATH)
     declared = declared_symbols()
-    assert len(declared) == 12 + 39 * 4
+    assert len(declared) == 23 + 53 * 4  # 23 global (9 of them fl_ctx_*) + 53 per element type (14 of them fl_ctx_host_*)
     for name in sorted(declared):
         assert hasattr(L, name), f"{name} declared in include/fastlanes_b200.h but not exported"
     assert declared == set(_lib.exported_symbols())
