@@ -260,6 +260,21 @@ static cudaError_t do_select(const LaunchArgs& a) {
     // with direct loads there instead of adding the TMA landing buffer on top
     constexpr bool kTma = sizeof(T) == 2 || sizeof(T) == 4;
     const size_t smem = size_t(kThreads / 32) * select_stage_bytes<T>();
+    // FLB_SELECT=thread|lane: the thread that decoded a value compacts it (select_warp_kernel) or lane L compacts the 32
+    // values of bitmap word L after an index-order round trip through shared memory (select_lane_kernel); A/B measurement
+    static const bool lane_variant = [] {
+        const char* e = std::getenv("FLB_SELECT");
+        if (e && std::strcmp(e, "thread") == 0) return false;
+        return true;
+    }();
+    if (lane_variant) {
+        static SmemOptIn opt_in;
+        if (const cudaError_t attr = opt_in.ensure(select_lane_kernel<T, W, kTma>, smem); attr != cudaSuccess) return attr;
+        select_lane_kernel<T, W, kTma><<<grid, kThreads, smem, a.stream>>>(
+            static_cast<const char*>(a.in), static_cast<const unsigned char*>(a.bitmap), a.offsets, static_cast<T*>(a.out),
+            a.n_blocks, static_cast<const T*>(a.refs), T(a.ref_scalar));
+        return cudaGetLastError();
+    }
     static SmemOptIn opt_in;
     if (const cudaError_t attr = opt_in.ensure(select_warp_kernel<T, W, kTma>, smem); attr != cudaSuccess) return attr;
     select_warp_kernel<T, W, kTma><<<grid, kThreads, smem, a.stream>>>(

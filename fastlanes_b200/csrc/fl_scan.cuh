@@ -465,4 +465,113 @@ select_warp_kernel(const char* __restrict__ packed, const unsigned char* __restr
     }
 }
 
+// ---------------------------------------------------------------------------------------------------
+// select, LANE-PER-WORD variant (round 2, second step).  In select_warp_kernel a thread compacts the values it decoded:
+// per value an extraction, the reference add, a predicated STS and a predicated pointer bump, plus per row a shared
+// lookup of (bitmap word, prefix) — ~450 instructions per block, issue-bound (u8: 2.0 ms per 2^22 blocks).  Here the
+// decoded tile is first written to shared memory in INDEX order (= the unpacked block layout, one STS.128 per row,
+// XOR-swizzled per 128-byte line), and then lane L re-reads the 32 consecutive values of bitmap word L — the word and
+// its exclusive prefix are already in L's registers from the popcount scan.  Compaction is then 32 x (predicated STS +
+// predicated bump) per lane with no lookups, the staging buffer is the same shared region (all lanes have their values
+// in registers before the first compacted store), and the reference add moves to the 16-byte drain (SWAR, selected
+// values only).
+// ---------------------------------------------------------------------------------------------------
+// swizzle of the 16-byte chunk index inside 128-byte line `line`: makes the lane-per-word re-read conflict-free
+// (u8: a lane owns 2 chunks, 4 lanes per line; u16: 4 chunks, 2 lanes per line; u32: a whole line; u64: two lines)
+template <class T>
+__device__ __forceinline__ int select_swz(int line) {
+    if constexpr (sizeof(T) == 1) return line & 1;
+    else if constexpr (sizeof(T) == 2) return line & 3;
+    else if constexpr (sizeof(T) == 4) return line & 7;
+    else return (line >> 1) & 7;
+}
+
+template <class T, int W, bool TMA>
+__global__ void __launch_bounds__(kThreads)
+select_lane_kernel(const char* __restrict__ packed, const unsigned char* __restrict__ bitmap,
+                   const uint64_t* __restrict__ offsets, T* __restrict__ out, size_t n_blocks,
+                   const T* __restrict__ refs, T ref_scalar) {
+    using WL = WarpLay<T>;
+    using R = typename Lay<T>::R;
+    constexpr int TB = Lay<T>::TB;
+    constexpr int RPG = WL::RPG;
+    constexpr int S = int(sizeof(T));
+    constexpr int EPV = 16 / S;       // elements per 16-byte vector
+    constexpr int NV = 32 * S / 16;   // 16-byte vectors holding the 32 values of one bitmap word
+    constexpr int LPR = Lay<T>::LPR;  // values per SWAR register
+    const size_t blk = (size_t(blockIdx.x) * kThreads + threadIdx.x) >> 5;
+    if (blk >= n_blocks) return;  // warp-uniform
+    const int lane = threadIdx.x & 31;
+    const int g = lane >> 3, j = lane & 7;
+    const int q = WL::rank_of_group(g);
+    // independent loads first (before the decode's TMA wait)
+    const uint32_t mword = reinterpret_cast<const uint32_t*>(bitmap + blk * 128)[lane];
+    const uint64_t obase = offsets[blk];
+    const T ref = refs ? refs[blk] : ref_scalar;
+    const uint32_t cnt = uint32_t(__popc(mword));
+    uint32_t incl = cnt;
+#pragma unroll
+    for (int d = 1; d < 32; d <<= 1) {
+        const uint32_t t = __shfl_up_sync(0xffffffffu, incl, d);
+        if (lane >= d) incl += t;
+    }
+    const uint32_t total = __shfl_sync(0xffffffffu, incl, 31);
+    if (total == 0) return;  // nothing selected in this block: skip the decode
+
+    Slice<T> v[RPG];
+    warp_decode_tile<T, W, TMA>(packed + blk * (size_t(128) * W), lane, q, j, v);
+
+    extern __shared__ __align__(16) unsigned char select_stage_smem[];
+    unsigned char* buf = select_stage_smem + (threadIdx.x >> 5) * select_stage_bytes<T>();
+    // 1) the decoded tile in index order: row r of the block is 128-byte line index(r, 0) * S / 128 (macros.rs:20-24)
+    seq_rows<RPG>([&](auto ic) {
+        constexpr int i = decltype(ic)::value;
+        const int line = warp_row_offset<T, i>(q) >> 7;
+        *reinterpret_cast<uint4*>(buf + line * 128 + ((j ^ select_swz<T>(line)) << 4)) = from_slice<T>(v[i]);
+    });
+    __syncwarp();
+    // 2) lane L takes the 32 values of bitmap word L: bytes [32*S*L, 32*S*(L+1)) of the tile
+    Slice<T> x[NV];
+#pragma unroll
+    for (int k = 0; k < NV; ++k) {
+        const int a = lane * (32 * S) + k * 16;
+        const int line = a >> 7, c = (a >> 4) & 7;
+        x[k] = to_slice<T>(*reinterpret_cast<const uint4*>(buf + line * 128 + ((c ^ select_swz<T>(line)) << 4)));
+    }
+    __syncwarp();  // every lane holds its values: the region is now the compaction target
+    T* o = out + obase;
+    const uint32_t mis = uint32_t((reinterpret_cast<uintptr_t>(o) & 15u) / sizeof(T));  // phase of the run inside a 16-byte vector
+    T* stage = reinterpret_cast<T*>(buf) + mis;
+    T* sp = stage + (incl - cnt);
+#pragma unroll
+    for (int k = 0; k < NV; ++k) {
+#pragma unroll
+        for (int e = 0; e < EPV; ++e) {
+            if (mword & (1u << (k * EPV + e))) {  // predicated STS + predicated pointer bump
+                *sp = T(x[k].r[e / LPR] >> (TB * (e % LPR)));
+                ++sp;
+            }
+        }
+    }
+    __syncwarp();
+    // 3) drain: stage - mis and o - mis are both 16-byte aligned; the FoR reference is added here (ffor.rs:47)
+    const Slice<T> rs = slice_splat<T>(ref);
+    const T* sbase = stage - mis;
+    T* gbase = o - mis;
+    const uint32_t end = mis + total;
+    const uint32_t nvec = (end + EPV - 1) / EPV;
+    for (uint32_t xv = lane; xv < nvec; xv += 32) {
+        const uint32_t lo = xv * EPV;
+        if (lo >= mis && lo + EPV <= end) {
+            const Slice<T> val = slice_add<T>(to_slice<T>(*reinterpret_cast<const uint4*>(sbase + lo)), rs);
+            stg128_stream(gbase + lo, from_slice<T>(val));
+        } else {
+#pragma unroll
+            for (int e = 0; e < EPV; ++e)
+                if (lo + e >= mis && lo + e < end) gbase[lo + e] = T(sbase[lo + e] + ref);
+        }
+    }
+    (void)sizeof(R);
+}
+
 }  // namespace flb

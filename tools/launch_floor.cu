@@ -1,0 +1,78 @@
+// launch_floor.cu — where do the microseconds of a single-block host call go?  (VERDICT r01 item 9 asks for <= 10 us.)
+// Times, on one non-blocking stream, the building blocks the low-latency host path is made of.
+//   build: nvcc -O2 -std=c++17 -gencode arch=compute_100a,code=sm_100a -o build/launch_floor tools/launch_floor.cu -lcuda
+#include <cuda.h>
+#include <cuda_runtime.h>
+
+#include <algorithm>
+#include <chrono>
+#include <cstdio>
+#include <cstring>
+#include <vector>
+
+#define CK(x) do { cudaError_t e_ = (x); if (e_ != cudaSuccess) { std::printf("CUDA error %s line %d\n", cudaGetErrorString(e_), __LINE__); return 1; } } while (0)
+
+__global__ void k_empty() {}
+// 32 threads: read `in_words` uint4 from `in`, write 128 uint4 (2 KiB) to `out`; optionally raise a flag at the end
+__global__ void k_copy(const uint4* __restrict__ in, uint4* __restrict__ out, int in_words, volatile unsigned* flag, unsigned seq) {
+    uint4 acc = make_uint4(0, 0, 0, 0);
+    for (int i = threadIdx.x; i < in_words; i += 32) { uint4 v = in[i]; acc.x ^= v.x; acc.y ^= v.y; acc.z ^= v.z; acc.w ^= v.w; }
+    for (int i = threadIdx.x; i < 128; i += 32) out[i] = acc;
+    if (flag) {
+        __threadfence_system();
+        __syncwarp();
+        if (threadIdx.x == 0) *flag = seq;
+    }
+}
+
+template <class F>
+static double med(F&& f, int iters = 3000) {
+    for (int i = 0; i < 100; ++i) f();
+    std::vector<double> t(iters);
+    for (int i = 0; i < iters; ++i) {
+        auto a = std::chrono::steady_clock::now();
+        f();
+        t[i] = std::chrono::duration<double, std::micro>(std::chrono::steady_clock::now() - a).count();
+    }
+    std::sort(t.begin(), t.end());
+    return t[iters / 2];
+}
+
+int main() {
+    CK(cudaSetDevice(0));
+    cudaStream_t st;
+    CK(cudaStreamCreateWithFlags(&st, cudaStreamNonBlocking));
+    char* h = nullptr;
+    CK(cudaHostAlloc(reinterpret_cast<void**>(&h), 1 << 16, cudaHostAllocDefault));
+    std::memset(h, 1, 1 << 16);
+    char* d = nullptr;
+    CK(cudaMalloc(&d, 1 << 16));
+    volatile unsigned* flag = reinterpret_cast<volatile unsigned*>(h + 32768);
+    *flag = 0;
+    unsigned seq = 0;
+    cudaEvent_t ev;
+    CK(cudaEventCreateWithFlags(&ev, cudaEventDisableTiming));
+    const uint4* hin = reinterpret_cast<const uint4*>(h);
+    uint4* hout = reinterpret_cast<uint4*>(h + 8192);
+
+    std::printf("A empty kernel + cudaStreamSynchronize                         %7.2f us\n", med([&] { k_empty<<<1, 32, 0, st>>>(); cudaStreamSynchronize(st); }));
+    std::printf("B kernel: 384 B from pinned host -> 2 KiB to pinned host + sync %7.2f us\n", med([&] { k_copy<<<1, 32, 0, st>>>(hin, hout, 24, nullptr, 0); cudaStreamSynchronize(st); }));
+    std::printf("B' same, device in/out (no PCIe in the kernel) + sync           %7.2f us\n", med([&] { k_copy<<<1, 32, 0, st>>>(reinterpret_cast<uint4*>(d), reinterpret_cast<uint4*>(d + 8192), 24, nullptr, 0); cudaStreamSynchronize(st); }));
+    std::printf("C kernel raises a flag in pinned memory, CPU polls it           %7.2f us\n", med([&] {
+        ++seq; k_copy<<<1, 32, 0, st>>>(hin, hout, 24, flag, seq); while (*flag != seq) {} }));
+    cudaStreamSynchronize(st);
+    std::printf("E kernel + cudaEventRecord + cudaEventQuery spin                %7.2f us\n", med([&] {
+        k_copy<<<1, 32, 0, st>>>(hin, hout, 24, nullptr, 0); cudaEventRecord(ev, st); while (cudaEventQuery(ev) == cudaErrorNotReady) {} }));
+    CUdeviceptr dflag = 0;
+    if (cuMemHostGetDevicePointer(&dflag, const_cast<unsigned*>(flag), 0) == CUDA_SUCCESS) {
+        std::printf("D kernel + cuStreamWriteValue32(flag), CPU polls                %7.2f us\n", med([&] {
+            ++seq; k_copy<<<1, 32, 0, st>>>(hin, hout, 24, nullptr, 0); cuStreamWriteValue32(st, dflag, seq, CU_STREAM_WRITE_VALUE_DEFAULT); while (*flag != seq) {} }));
+    }
+    cudaStreamSynchronize(st);
+    std::printf("F memcpyAsync H2D 384 B + kernel (device in, pinned out) + sync %7.2f us\n", med([&] {
+        cudaMemcpyAsync(d, h, 384, cudaMemcpyHostToDevice, st); k_copy<<<1, 32, 0, st>>>(reinterpret_cast<uint4*>(d), hout, 24, nullptr, 0); cudaStreamSynchronize(st); }));
+    std::printf("G round-1 path: H2D 384 B + kernel + D2H 2 KiB + sync           %7.2f us\n", med([&] {
+        cudaMemcpyAsync(d, h, 384, cudaMemcpyHostToDevice, st); k_copy<<<1, 32, 0, st>>>(reinterpret_cast<uint4*>(d), reinterpret_cast<uint4*>(d + 8192), 24, nullptr, 0);
+        cudaMemcpyAsync(h + 8192, d + 8192, 2048, cudaMemcpyDeviceToHost, st); cudaStreamSynchronize(st); }));
+    return 0;
+}
