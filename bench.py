@@ -367,6 +367,40 @@ def other_configs(D: Dev, packed, out, peak, steps, log2_total):
         "launches_per_gpu": len(list(waves(b1 - b0, wb)))}
     del p16, o16
     torch.cuda.empty_cache()
+    # Result check of the SHARDED path (not only its speed): a deterministic 2^18-block W=16 column defined by block
+    # index alone; every rank decodes its contiguous shard, the wrapping int64 sums are all-reduced (the only collective
+    # that ever touches decoded data: 8 bytes per rank) and must equal the sum of the whole column decoded by one GPU.
+    # Sampled blocks at the shard boundaries go to the host for the oracle comparison in the cpu_baseline leg.
+    nv = 1 << 18
+    v0, v1 = block_shard(nv, D.rank, D.world)
+
+    def column(bfirst, bend):  # packed words of blocks [bfirst, bend): an LCG of the global word index
+        idx = torch.arange(bfirst * 32 * W, bend * 32 * W, dtype=torch.int64, device=D.dev)
+        return ((idx * 6364136223846793005 + 1442695040888963407) >> 29).to(torch.int32)
+
+    mine_p = column(v0, v1)
+    mine_o = torch.empty((v1 - v0) * 1024, dtype=torch.int32, device=D.dev)
+    if v1 > v0:
+        D.call("fl_unpack", 32, W, v1 - v0, mine_p.data_ptr(), mine_o.data_ptr(), D.sp)
+    from fastlanes_b200.shard import sum_over_ranks
+
+    mask63 = (1 << 63) - 1
+    part = int(mine_o.to(torch.int64).sum().item()) & mask63
+    sharded_sum = sum_over_ranks(part, D.dist, D.dev) & mask63
+    whole_p = column(0, nv)
+    whole_o = torch.empty(nv * 1024, dtype=torch.int32, device=D.dev)
+    D.call("fl_unpack", 32, W, nv, whole_p.data_ptr(), whole_o.data_ptr(), D.sp)
+    whole_sum = int(whole_o.to(torch.int64).sum().item()) & mask63
+    assert sharded_sum == whole_sum, "sharded decode: all-reduced checksum differs from the single-GPU decode"
+    sample = sorted({0, nv - 1, *[block_shard(nv, r, D.world)[0] for r in range(D.world)], *[max(0, block_shard(nv, r, D.world)[1] - 1) for r in range(D.world)]})
+    res["sharded_verify"] = {"config": "2^18-block u32 W=16 column, contiguous shards, all-reduced checksum of the decoded shards vs one GPU decoding the whole column",
+                             "checksum_sharded": sharded_sum, "checksum_one_gpu": whole_sum, "match": sharded_sum == whole_sum,
+                             "sampled_blocks": sample}
+    res["_samples"] = {"width": W, "blocks": sample,
+                       "packed": [whole_p[b * 32 * W:(b + 1) * 32 * W].cpu().numpy() for b in sample],
+                       "decoded": [whole_o[b * 1024:(b + 1) * 1024].cpu().numpy() for b in sample]}
+    del mine_p, mine_o, whole_p, whole_o
+    torch.cuda.empty_cache()
     return res
 
 
@@ -627,9 +661,10 @@ def main():
             except Exception:
                 pass
 
-    other = None
+    other, samples = None, None
     if not args.no_other:
         other = other_configs(D, packed, out, peak, args.steps, args.log2_total_blocks)
+        samples = other.pop("_samples")
         if world == 1 and not args.no_ops:
             other["ops"] = ops_table(D, peak)
             other["min_frac_over_ops"] = other["ops"]["min_frac_over_ops"]
@@ -650,6 +685,11 @@ def main():
         dt, ints = cpu_sweep(oracle, np, lg, threads, 3)
         dt1, ints1 = cpu_sweep(oracle, np, 13, 1, 2)
         fdt, fints = cpu_filter_sweep(oracle, np, lg, threads, 2)
+        if samples is not None:  # the oracle as checker of the sharded decode (sampled blocks at the shard boundaries)
+            ok = all(np.array_equal(oracle.unpack(p.view(np.uint32), samples["width"], n_blocks=1), d.view(np.uint32))
+                     for p, d in zip(samples["packed"], samples["decoded"]))
+            other["sharded_verify"]["oracle_sampled_blocks_match"] = bool(ok)
+            assert ok, "sharded decode disagrees with the oracle on sampled blocks"
         cpu = {"value": round(ints / dt / 1e9, 3), "unit": "Gint/s", "cores": threads, "kind": "port",
                "sample": f"u32 unpack W=1..32, 2^{lg} blocks per width (the whole config; best of 3 passes), host memory, {oracle.isa()}, {threads} threads (fastest probed; {hw} logical CPUs visible, cgroup CPU quota {quota})",
                "single_thread_Gints": round(ints1 / dt1 / 1e9, 3),

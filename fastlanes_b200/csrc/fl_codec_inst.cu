@@ -15,6 +15,27 @@
 #ifndef FLB_U8_ORIG_DEFAULT_SLICE
 #define FLB_U8_ORIG_DEFAULT_SLICE 1  // measured: 6.5-7.1 TB/s vs 4.6-6.4 (profiles/opbench_u8orig_r01.txt)
 #endif
+#ifndef FLB_U16_ORIG_SLICE_W
+#define FLB_U16_ORIG_SLICE_W 16  // widths up to this have the row-slice instantiation of the u16 fused original-order chains (A/B at every width)
+#endif
+#ifndef FLB_U16_ORIG_DEFAULT_SLICE
+#define FLB_U16_ORIG_DEFAULT_SLICE 0
+#endif
+#ifndef FLB_U8_DELTA_W8_DEFAULT_SLICE
+#define FLB_U8_DELTA_W8_DEFAULT_SLICE 1  // measured: 1375 vs 1408 us per 2^22 blocks (profiles/opbench_u8_delta_w8_r02.txt)
+#endif
+#ifndef FLB_ORIG_OCC_W
+#define FLB_ORIG_OCC_W 4  // widths up to this have the extra-occupancy instantiation of the fused original-order decode
+#endif
+#ifndef FLB_ORIG_OCC_DEFAULT
+#define FLB_ORIG_OCC_DEFAULT 1
+#endif
+#ifndef FLB_U16_FILTER_DEFAULT_SLICE
+#define FLB_U16_FILTER_DEFAULT_SLICE 1
+#endif
+#ifndef FLB_AUTO_SLICE_DEFAULT
+#define FLB_AUTO_SLICE_DEFAULT 1
+#endif
 #if FLB_PART == 3
 #include "fl_scan.cuh"
 #endif
@@ -51,9 +72,35 @@ using launch_fn = cudaError_t (*)(const LaunchArgs&);
     return v;
 }
 
+// u16 fused original-order chains at small W: FLB_U16_ORIG=warp|slice (A/B; default = measured best)
+[[maybe_unused]] static inline bool u16_orig_slice() {
+    static const bool v = [] {
+        const char* e = std::getenv("FLB_U16_ORIG");
+        if (e && std::strcmp(e, "warp") == 0) return false;
+        if (e && std::strcmp(e, "slice") == 0) return true;
+        return FLB_U16_ORIG_DEFAULT_SLICE != 0;
+    }();
+    return v;
+}
+
 #if FLB_PART == 0
 template <class T, int W, int OP>
 static cudaError_t do_unpack(const LaunchArgs& a) {
+    if constexpr (sizeof(T) == 1 && OP == UOP_DELTA && W == 8) {
+        // u8 at W = 8 (verbatim rows): FLB_U8_DELTA_W8=slice|warp, A/B; default = measured best
+        static const bool slice = [] {
+            const char* e = std::getenv("FLB_U8_DELTA_W8");
+            if (e && std::strcmp(e, "slice") == 0) return true;
+            if (e && std::strcmp(e, "warp") == 0) return false;
+            return FLB_U8_DELTA_W8_DEFAULT_SLICE != 0;
+        }();
+        if (slice) {
+            unpack_kernel<T, W, OP><<<grid_for(a.n_blocks), kThreads, 0, a.stream>>>(
+                static_cast<const char*>(a.in), static_cast<char*>(a.out), a.n_blocks, static_cast<const T*>(a.refs),
+                T(a.ref_scalar), static_cast<const char*>(a.base));
+            return cudaGetLastError();
+        }
+    }
     if constexpr (sizeof(T) == 1 && OP == UOP_DELTA && W < 8) {
         // u8 fused delta at W < 8: a 1 KiB block gives a warp too little work to amortise the 4-group shuffle
         // scan (ALU-bound, 5.1-6.1 TB/s); the row-slice kernel keeps the whole 8-row chain in one thread
@@ -62,6 +109,13 @@ static cudaError_t do_unpack(const LaunchArgs& a) {
             static_cast<const char*>(a.in), static_cast<char*>(a.out), a.n_blocks, static_cast<const T*>(a.refs),
             T(a.ref_scalar), static_cast<const char*>(a.base));
         return cudaGetLastError();
+    }
+    if constexpr (sizeof(T) == 2 && OP == UOP_DELTA_ORIG && W <= FLB_U16_ORIG_SLICE_W) {
+        if (u16_orig_slice()) {
+            undelta_orig_u16_slice_kernel<W><<<grid_for(a.n_blocks), kThreads, 0, a.stream>>>(
+                static_cast<const char*>(a.in), static_cast<char*>(a.out), a.n_blocks, static_cast<const char*>(a.base));
+            return cudaGetLastError();
+        }
     }
     if constexpr (sizeof(T) == 1 && OP == UOP_DELTA_ORIG) {
         if (u8_orig_slice()) {
@@ -83,6 +137,26 @@ static cudaError_t do_unpack(const LaunchArgs& a) {
         smem = size_t(kThreads / 32) * 128 * Lay<T>::TB;
         static SmemOptIn opt_in;
         if (const cudaError_t attr = opt_in.ensure(unpack_warp_kernel<T, W, OP, kTma>, smem); attr != cudaSuccess) return attr;
+    }
+    if constexpr (OP == UOP_DELTA_ORIG && sizeof(T) >= 2 && W <= FLB_ORIG_OCC_W) {
+        // Small W: the kernel is latency-bound (ncu u32 W=1: 72 registers -> 3 CTAs per SM, 31 % of the warps resident,
+        // DRAM 71 %, profiles/ncu_r02_kernels.md).  A second instantiation whose launch bound holds the compiler to more
+        // resident CTAs (u32: 4 = 64 registers; u64: 3 = the shared-memory limit; u16: 6 = 40 registers) is launched
+        // instead.  Measured (profiles/opbench_orig_occ_r02.txt): u32 W=1 811 -> 702 us, u64 W=1 779 -> 710 us.
+        // FLB_ORIG_OCC=0|1|2: off / u32 + u64 / also u16 (A/B; default = measured best).
+        static const int occ = [] {
+            const char* e = std::getenv("FLB_ORIG_OCC");
+            return (e && e[0] >= '0' && e[0] <= '2') ? e[0] - '0' : FLB_ORIG_OCC_DEFAULT;
+        }();
+        if ((occ >= 1 && sizeof(T) >= 4) || occ == 2) {
+            constexpr int kMinB = sizeof(T) == 2 ? 6 : (sizeof(T) == 4 ? 4 : 3);
+            static SmemOptIn opt_in2;
+            if (const cudaError_t attr = opt_in2.ensure(unpack_warp_kernel<T, W, OP, kTma, false, kMinB>, smem); attr != cudaSuccess) return attr;
+            unpack_warp_kernel<T, W, OP, kTma, false, kMinB><<<grid, kThreads, smem, a.stream>>>(
+                static_cast<const char*>(a.in), static_cast<char*>(a.out), a.n_blocks, static_cast<const T*>(a.refs),
+                T(a.ref_scalar), static_cast<const char*>(a.base));
+            return cudaGetLastError();
+        }
     }
     unpack_warp_kernel<T, W, OP, kTma><<<grid, kThreads, smem, a.stream>>>(
         static_cast<const char*>(a.in), static_cast<char*>(a.out), a.n_blocks, static_cast<const T*>(a.refs),
@@ -134,6 +208,13 @@ cudaError_t launch_unpack<elem_t>(int op, const LaunchArgs& a) {
 #elif FLB_PART == 1
 template <class T, int W, int OP>
 static cudaError_t do_pack(const LaunchArgs& a) {
+    if constexpr (sizeof(T) == 2 && OP == POP_ORIG_DELTA && W <= FLB_U16_ORIG_SLICE_W) {
+        if (u16_orig_slice()) {
+            orig_delta_pack_u16_slice_kernel<W><<<grid_for(a.n_blocks), kThreads, 0, a.stream>>>(
+                static_cast<const char*>(a.in), static_cast<char*>(a.out), a.n_blocks, static_cast<const char*>(a.base));
+            return cudaGetLastError();
+        }
+    }
     if constexpr (sizeof(T) == 1 && OP == POP_ORIG_DELTA) {
         if (u8_orig_slice()) {
             orig_delta_pack_u8_slice_kernel<W><<<grid_for(a.n_blocks), kThreads, 0, a.stream>>>(
@@ -155,6 +236,22 @@ static cudaError_t do_pack(const LaunchArgs& a) {
         if (mode == 1 || (mode < 0 && (OP == POP_FOR || W < 2))) {
             pack_kernel<T, W, OP><<<grid_for(a.n_blocks), kThreads, 0, a.stream>>>(
                 static_cast<const char*>(a.in), static_cast<char*>(a.out), a.n_blocks, static_cast<const T*>(a.refs), T(a.ref_scalar));
+            return cudaGetLastError();
+        }
+    }
+    if constexpr (sizeof(T) <= 2 && OP == POP_FOR_AUTO) {
+        // fused statistics + FoR for u8 / u16: FLB_AUTO_SLICE=0|1|2 selects the warp-block kernel (0), the row-slice kernel
+        // where it measured faster (1: u8 below W = 8, u16 at W <= 2) or for u8 and u16 at every width (2); A/B
+        static const int mode = [] {
+            const char* e = std::getenv("FLB_AUTO_SLICE");
+            return (e && e[0] >= '0' && e[0] <= '2') ? e[0] - '0' : FLB_AUTO_SLICE_DEFAULT;
+        }();
+        // measured (profiles/opbench_auto_slice_r02.txt): u8 W < 8: 4.15-5.11 -> 6.56-6.78 TB/s; u16 W = 1: 5.76 -> 6.88,
+        // W = 4: 7.19 -> 6.84 (worse), W >= 9: equal within 2 %
+        if ((mode == 1 && ((sizeof(T) == 1 && W < 8) || (sizeof(T) == 2 && W <= 2))) || mode == 2) {
+            for_pack_auto_slice_kernel<T, W><<<grid_for(a.n_blocks), kThreads, 0, a.stream>>>(
+                static_cast<const char*>(a.in), static_cast<char*>(a.out), a.n_blocks, static_cast<T*>(a.refs_out),
+                static_cast<T*>(a.spans_out));
             return cudaGetLastError();
         }
     }
@@ -239,6 +336,21 @@ static cudaError_t do_filter(const LaunchArgs& a) {
             return cudaGetLastError();
         }
     }
+    if constexpr (sizeof(T) == 2 && W > 0 && W < 16) {
+        // u16: FLB_U16_FILTER=warp|slice (A/B; default = measured best)
+        static const bool slice = [] {
+            const char* e = std::getenv("FLB_U16_FILTER");
+            if (e && std::strcmp(e, "warp") == 0) return false;
+            if (e && std::strcmp(e, "slice") == 0) return true;
+            return FLB_U16_FILTER_DEFAULT_SLICE != 0;
+        }();
+        if (slice) {
+            filter_u16_slice_kernel<W><<<grid_for(a.n_blocks), kThreads, 0, a.stream>>>(
+                static_cast<const char*>(a.in), static_cast<unsigned char*>(a.out), a.counts, a.n_blocks,
+                static_cast<const uint16_t*>(a.refs), uint16_t(a.ref_scalar), uint16_t(a.flo), uint16_t(a.fhi));
+            return cudaGetLastError();
+        }
+    }
     // blocks per warp: 4 amortises the per-warp set-up while the filter is issue-bound (u32 W=8: 285 -> 208 us); only the
     // verbatim width W = T of u16/u32/u64 measured (slightly) faster with one block per warp; u64 W=61 loses 25 % with one
     // (profiles/opbench_scan_r01.txt)
@@ -262,11 +374,15 @@ static cudaError_t do_select(const LaunchArgs& a) {
     const size_t smem = size_t(kThreads / 32) * select_stage_bytes<T>();
     // FLB_SELECT=thread|lane: the thread that decoded a value compacts it (select_warp_kernel) or lane L compacts the 32
     // values of bitmap word L after an index-order round trip through shared memory (select_lane_kernel); A/B measurement
-    static const bool lane_variant = [] {
+    // measured at 25 % selectivity (profiles/opbench_select_r02.txt): lane is faster for u8 (1.82-1.99 vs 2.07-2.53 ms per
+    // 2^22 blocks) and for u64 above W ~ 32 (W=64: 0.97 vs 1.65 ms); thread for u16 / u32 and narrow u64
+    static const int forced = [] {
         const char* e = std::getenv("FLB_SELECT");
-        if (e && std::strcmp(e, "thread") == 0) return false;
-        return true;
+        if (e && std::strcmp(e, "thread") == 0) return 0;
+        if (e && std::strcmp(e, "lane") == 0) return 1;
+        return -1;
     }();
+    const bool lane_variant = forced >= 0 ? forced == 1 : (sizeof(T) == 1 || (sizeof(T) == 8 && W > 32));
     if (lane_variant) {
         static SmemOptIn opt_in;
         if (const cudaError_t attr = opt_in.ensure(select_lane_kernel<T, W, kTma>, smem); attr != cudaSuccess) return attr;

@@ -226,7 +226,8 @@ template <class T>
 __device__ __forceinline__ int orig_tile_swizzle(int A) {
     if constexpr (sizeof(T) == 4) return A ^ ((((A >> 7) & 1) | (((A >> 10) & 3) << 1)) << 4);
     else if constexpr (sizeof(T) == 8) return A ^ (((A >> 10) & 7) << 4);
-    else return A;  // u8/u16 scatter 2-/8-byte pieces: no 16-byte bank-group structure to fix
+    else if constexpr (sizeof(T) == 2) return A ^ (((A >> 10) & 1) << 4);  // see orig_tile_scatter (u16)
+    else return A;  // u8 scatters 2-byte pieces: no bank-group structure to fix
 }
 
 // register tile v[row].r[..]  ->  warp-private shared tile in ORIGINAL order (this thread's lanes, its run of rows)
@@ -243,14 +244,18 @@ __device__ __forceinline__ void orig_tile_scatter(unsigned char* tile, const Sli
                 *reinterpret_cast<uint4*>(tile + orig_tile_swizzle<T>(A0 + m * 16)) = gather_rows_chunk<T, RPG>(v, r, m);
         }
     } else if constexpr (sizeof(T) == 2) {
-        // RPG = 4 rows x 8 lanes: per lane 4 consecutive u16 = 8 bytes
+        // RPG = 4 rows x 8 lanes: per lane 4 consecutive u16 = 8 bytes at A = 128*(8(j&1) + k) + 16*FL_ORDER[j>>1] + 8q.
+        // A 64-bit shared access is served per HALF-warp (two row groups q): its 16 lanes hit 4*FL_ORDER[j>>1] + 2q (+1),
+        // 16 distinct 8-byte bank pairs, but j&1 (address bit 10) maps two lanes onto each pair: a 2-way conflict on
+        // every STS.64 / LDS.64 (ncu: 16.8 M extra wavefronts per 2^20 blocks, profiles/ncu_r02_kernels.md).  Bit 4 (the
+        // 16-byte bank group, = bit 2 of q's contribution, constant inside a half-warp) is XORed with bit 10.
 #pragma unroll
         for (int k = 0; k < 8; ++k) {
             const uint32_t sel = (k & 1) ? 0x7632u : 0x5410u;
             uint2 p;
             p.x = __byte_perm(v[0].r[k >> 1], v[1].r[k >> 1], sel);
             p.y = __byte_perm(v[2].r[k >> 1], v[3].r[k >> 1], sel);
-            *reinterpret_cast<uint2*>(tile + orig_run_byte_offset<T>(q, j, k)) = p;
+            *reinterpret_cast<uint2*>(tile + orig_tile_swizzle<T>(orig_run_byte_offset<T>(q, j, k))) = p;
         }
     } else {
         // RPG = 2 rows x 16 lanes: per lane 2 consecutive u8 = 2 bytes
@@ -278,8 +283,8 @@ __device__ __forceinline__ void orig_tile_gather(const unsigned char* tile, Slic
     } else if constexpr (sizeof(T) == 2) {
 #pragma unroll
         for (int rr = 0; rr < 4; ++rr) {
-            const uint2 a = *reinterpret_cast<const uint2*>(tile + orig_run_byte_offset<T>(q, j, 2 * rr));
-            const uint2 b = *reinterpret_cast<const uint2*>(tile + orig_run_byte_offset<T>(q, j, 2 * rr + 1));
+            const uint2 a = *reinterpret_cast<const uint2*>(tile + orig_tile_swizzle<T>(orig_run_byte_offset<T>(q, j, 2 * rr)));
+            const uint2 b = *reinterpret_cast<const uint2*>(tile + orig_tile_swizzle<T>(orig_run_byte_offset<T>(q, j, 2 * rr + 1)));
             v[0].r[rr] = __byte_perm(a.x, b.x, 0x5410u);
             v[1].r[rr] = __byte_perm(a.x, b.x, 0x7632u);
             v[2].r[rr] = __byte_perm(a.y, b.y, 0x5410u);
@@ -450,8 +455,8 @@ __device__ __forceinline__ void warp_decode_tile(const char* __restrict__ blk_pa
 template <class T, int OP, int W>
 constexpr int unpack_min_ctas() { return (sizeof(T) == 8 && OP == UOP_DELTA && W < FLB_U64_DELTA_OCC_W) ? 3 : 1; }
 
-template <class T, int W, int OP, bool TMA = false, bool LINEAR = false>
-__global__ void __launch_bounds__(kThreads, unpack_min_ctas<T, OP, W>())
+template <class T, int W, int OP, bool TMA = false, bool LINEAR = false, int MINB = unpack_min_ctas<T, OP, W>()>
+__global__ void __launch_bounds__(kThreads, MINB)
 unpack_warp_kernel(const char* __restrict__ packed, char* __restrict__ out, size_t n_blocks,
                    const T* __restrict__ refs, T ref_scalar, const char* __restrict__ base) {
     using R = typename Lay<T>::R;
@@ -912,6 +917,92 @@ pack_kernel(const char* __restrict__ in, char* __restrict__ packed, size_t n_blo
 }
 
 // ---------------------------------------------------------------------------------------------------
+// for_pack with reference = the block's own minimum (POP_FOR_AUTO), ROW-SLICE mapping for the small element types.
+// In the warp-block kernel a u8 block (1 KiB) gives a thread two rows: the statistics are a 5-step, 2-register
+// butterfly per 1 KiB, and the cross-group merge of the packed words comes on top (4.2-4.8 TB/s at W < 8,
+// profiles/opbench_r01.txt).  With 8 threads per block a thread holds ALL rows of its 16-byte column slice: min / max are
+// a register reduction plus a 3-step butterfly inside the 8-thread group, and packing is the shuffle-free register
+// chain of pack_slice (src/macros.rs:62-94).  refs_out / spans_out as in pack_warp_kernel.
+// ---------------------------------------------------------------------------------------------------
+template <class T, int W>
+__global__ void __launch_bounds__(kThreads)
+for_pack_auto_slice_kernel(const char* __restrict__ in, char* __restrict__ packed, size_t n_blocks,
+                           T* __restrict__ refs_out, T* __restrict__ spans_out) {
+    using R = typename Lay<T>::R;
+    constexpr int TB = Lay<T>::TB;
+    constexpr int NR = Lay<T>::NR;
+    static_assert(sizeof(T) <= 2, "row-slice statistics kernel: u8 / u16");
+    const size_t tid = size_t(blockIdx.x) * kThreads + threadIdx.x;
+    const size_t blk_raw = tid / kSlicesPerBlock;
+    const int j = int(tid % kSlicesPerBlock);
+    const bool active = blk_raw < n_blocks;  // whole 8-thread groups are active or not; the shuffles stay inside a group
+    const size_t blk = active ? blk_raw : 0;
+    const char* ip = in + blk * (size_t(128) * TB) + j * 16;
+    Slice<T> src[TB];
+    seq_rows<TB>([&](auto rc) {
+        constexpr int r = decltype(rc)::value;
+        src[r] = load_slice<T>(ip + row_byte_offset<T>(r));
+    });
+    // statistics: both types reduce as 16x2 vectors (u8: even / odd bytes, see u8_minmax_acc)
+    uint32_t lo, hi;
+    if constexpr (sizeof(T) == 1) {
+        uint32_t mn_e = 0x00FF00FFu, mn_o = 0x00FF00FFu, mx_e = 0, mx_o = 0;
+#pragma unroll
+        for (int r = 0; r < TB; ++r)
+#pragma unroll
+            for (int i = 0; i < NR; ++i) u8_minmax_acc(src[r].r[i], mn_e, mn_o, mx_e, mx_o);
+        lo = __vminu2(mn_e, mn_o); hi = __vmaxu2(mx_e, mx_o);
+    } else {
+        lo = src[0].r[0]; hi = lo;
+#pragma unroll
+        for (int r = 0; r < TB; ++r)
+#pragma unroll
+            for (int i = 0; i < NR; ++i) { lo = __vminu2(lo, src[r].r[i]); hi = __vmaxu2(hi, src[r].r[i]); }
+    }
+#pragma unroll
+    for (int d = 4; d >= 1; d >>= 1) {
+        lo = __vminu2(lo, __shfl_xor_sync(0xffffffffu, lo, d));
+        hi = __vmaxu2(hi, __shfl_xor_sync(0xffffffffu, hi, d));
+    }
+    const T mn = T(min(lo & 0xFFFFu, lo >> 16)), mx = T(max(hi & 0xFFFFu, hi >> 16));
+    if (active && j == 0) {
+        refs_out[blk] = mn;
+        if (spans_out != nullptr) spans_out[blk] = T(mx - mn);
+    }
+    if constexpr (W == 0) return;  // macros.rs:52: nothing to store
+    if (!active) return;
+    const Slice<T> ref = slice_splat<T>(mn);
+    char* pk = packed + blk * (size_t(128) * W) + j * 16;
+    Slice<T> tmp = slice_zero<T>();
+    seq_rows<TB>([&](auto rc) {
+        constexpr int row = decltype(rc)::value;
+        Slice<T> s = slice_sub<T>(src[row], ref);  // ffor.rs:33
+        if constexpr (W == TB) {
+            store_slice<T>(pk + row * 128, s);  // macros.rs:54-59
+        } else {
+            constexpr int shift = (row * W) % TB;
+            constexpr int curr = (row * W) / TB;        // macros.rs:84
+            constexpr int next = ((row + 1) * W) / TB;  // macros.rs:85
+            constexpr R MW = rep_mask<T>(W);
+#pragma unroll
+            for (int i = 0; i < NR; ++i) {
+                const R v = s.r[i] & MW;  // macros.rs:73
+                if constexpr (shift == 0) tmp.r[i] = v;
+                else if constexpr (shift + W <= TB) tmp.r[i] |= v << shift;
+                else tmp.r[i] |= lane_shl<T, shift>(v);  // macros.rs:79
+                s.r[i] = v;
+            }
+            if constexpr (next > curr) {  // macros.rs:88-92
+                store_slice<T>(pk + curr * 128, tmp);
+                constexpr int rem = ((row + 1) * W) % TB;
+#pragma unroll
+                for (int i = 0; i < NR; ++i) tmp.r[i] = lane_shr_keep<T, W - rem, rem>(s.r[i]);
+            }
+        }
+    });
+}
+
+// ---------------------------------------------------------------------------------------------------
 // a15 Delta::delta (src/delta.rs:24-33) and a16 Delta::undelta (src/delta.rs:36-45): per lane, along
 // rows in iterate! order (src/macros.rs:12-31).  in/out: n_blocks x (128*T bytes); base: n_blocks x 128 B.
 // ---------------------------------------------------------------------------------------------------
@@ -1069,6 +1160,126 @@ orig_delta_pack_u8_slice_kernel(const char* __restrict__ in, char* __restrict__ 
                 for (int i = 0; i < 4; ++i) tmp.r[i] = lane_shr_keep<T, W - rem, rem>(s.r[i]);
             }
         }
+    });
+}
+
+// ---------------------------------------------------------------------------------------------------
+// u16 fused original-order chains, ROW-SLICE layout, for SMALL W (round 2).  In the warp-block kernel a u16 block is
+// 2 KiB of output for a whole warp: at W <= 4 the fixed per-warp work (shuffle scan, 8 STS.64 + 4 LDS.128 through the
+// shared tile, MIO queue) leaves it latency-bound at 0.88-0.93 of the roofline (ncu: long_scoreboard + mio_throttle,
+// profiles/ncu_r02_kernels.md).  Same idea as the u8 kernels above: thread j of an 8-thread group owns lanes 8j..8j+7
+// for ALL 16 rows, so the delta chain is a register chain and, for every lane l, the 16 rows are the 16 CONSECUTIVE
+// originals start(l) .. start(l)+15 (src/transpose.rs:29-36 composed with src/macros.rs:20-24) = 32 contiguous bytes at
+//     2*start(l) = 128*(8*(j&1) + k) + 16*FL_ORDER[j>>1]          (l = 8j + k)
+// i.e. two 16-byte global accesses per lane, assembled from the row-major SWAR registers by PRMT.  Registers are
+// processed one SWAR register (two lanes) at a time to keep the live set at 16 rows.  No shared memory, no shuffles.
+// ---------------------------------------------------------------------------------------------------
+template <int W>
+__global__ void __launch_bounds__(kThreads)
+undelta_orig_u16_slice_kernel(const char* __restrict__ packed, char* __restrict__ out, size_t n_blocks,
+                              const char* __restrict__ base) {
+    using T = uint16_t;
+    using R = uint32_t;
+    constexpr int TB = 16;
+    const size_t tid = size_t(blockIdx.x) * kThreads + threadIdx.x;
+    const size_t blk = tid / kSlicesPerBlock;
+    const int j = int(tid % kSlicesPerBlock);
+    if (blk >= n_blocks) return;
+    const Slice<T> b0 = load_slice<T>(base + blk * 128 + j * 16);  // delta.rs:50
+    const char* pk = packed + blk * (size_t(128) * W) + j * 16;
+    Slice<T> w[W > 0 ? W : 1];
+    seq_rows<W>([&](auto kc) {
+        constexpr int k = decltype(kc)::value;
+        w[k] = load_slice<T>(pk + k * 128);
+    });
+    char* ob = out + blk * 2048 + 1024 * (j & 1) + 16 * fl_order_rt(j >> 1);
+#pragma unroll
+    for (int r = 0; r < 4; ++r) {
+        R prev = b0.r[r];
+        R v[TB];
+        seq_rows<TB>([&](auto rc) {
+            constexpr int row = decltype(rc)::value;
+            R x;
+            if constexpr (W == 0) x = 0;                 // macros.rs:118-125
+            else if constexpr (W == TB) x = w[row].r[r];  // macros.rs:126-132
+            else {
+                constexpr int curr = (row * W) / TB;
+                constexpr int nxt = (curr + 1 < W) ? curr + 1 : curr;
+                x = extract_field<T, W, row>(w[curr].r[r], w[nxt].r[r]);
+            }
+            prev = lane_add<T>(prev, x);  // delta.rs:58-60
+            v[row] = prev;
+        });
+#pragma unroll
+        for (int h = 0; h < 2; ++h) {  // lane k = 2r + h: its 16 rows = 8 words of two consecutive originals each
+            const uint32_t sel = h ? 0x7632u : 0x5410u;
+            uint32_t m[8];
+#pragma unroll
+            for (int i = 0; i < 8; ++i) m[i] = __byte_perm(v[2 * i], v[2 * i + 1], sel);
+            char* o = ob + 128 * (2 * r + h);
+            stg128_stream(o, make_uint4(m[0], m[1], m[2], m[3]));
+            stg128_stream(o + 16, make_uint4(m[4], m[5], m[6], m[7]));
+        }
+    }
+}
+
+// pack::<W>(delta(transpose(in), base)) for u16 at small W  (src/transpose.rs:11-15, src/delta.rs:24-33, src/macros.rs:35-97)
+template <int W>
+__global__ void __launch_bounds__(kThreads)
+orig_delta_pack_u16_slice_kernel(const char* __restrict__ in, char* __restrict__ packed, size_t n_blocks,
+                                 const char* __restrict__ base) {
+    using T = uint16_t;
+    using R = uint32_t;
+    constexpr int TB = 16;
+    if constexpr (W == 0) return;  // macros.rs:52
+    const size_t tid = size_t(blockIdx.x) * kThreads + threadIdx.x;
+    const size_t blk = tid / kSlicesPerBlock;
+    const int j = int(tid % kSlicesPerBlock);
+    if (blk >= n_blocks) return;
+    const Slice<T> b0 = load_slice<T>(base + blk * 128 + j * 16);  // delta.rs:26
+    const char* ib = in + blk * 2048 + 1024 * (j & 1) + 16 * fl_order_rt(j >> 1);
+    Slice<T> outw[W > 0 ? W : 1];
+#pragma unroll
+    for (int r = 0; r < 4; ++r) {
+        const uint4 a0 = ldg128_stream(ib + 128 * (2 * r)), a1 = ldg128_stream(ib + 128 * (2 * r) + 16);          // lane 2r
+        const uint4 c0 = ldg128_stream(ib + 128 * (2 * r + 1)), c1 = ldg128_stream(ib + 128 * (2 * r + 1) + 16);  // lane 2r+1
+        const uint32_t la[8] = {a0.x, a0.y, a0.z, a0.w, a1.x, a1.y, a1.z, a1.w};
+        const uint32_t lc[8] = {c0.x, c0.y, c0.z, c0.w, c1.x, c1.y, c1.z, c1.w};
+        R v[TB];
+#pragma unroll
+        for (int i = 0; i < 8; ++i) {  // word i of a lane = rows 2i, 2i+1
+            v[2 * i] = __byte_perm(la[i], lc[i], 0x5410u);
+            v[2 * i + 1] = __byte_perm(la[i], lc[i], 0x7632u);
+        }
+        R prev = b0.r[r];
+        R tmp = 0;
+        seq_rows<TB>([&](auto rc) {
+            constexpr int row = decltype(rc)::value;
+            R s = lane_sub<T>(v[row], prev);  // delta.rs:28-30
+            prev = v[row];
+            if constexpr (W == TB) {
+                outw[row].r[r] = s;  // macros.rs:54-59
+            } else {
+                constexpr int shift = (row * W) % TB;
+                constexpr int curr = (row * W) / TB;
+                constexpr int next = ((row + 1) * W) / TB;
+                constexpr R MW = rep_mask<T>(W);
+                const R x = s & MW;  // macros.rs:73
+                if constexpr (shift == 0) tmp = x;
+                else if constexpr (shift + W <= TB) tmp |= x << shift;
+                else tmp |= lane_shl<T, shift>(x);  // macros.rs:79
+                if constexpr (next > curr) {  // macros.rs:88-92
+                    outw[curr].r[r] = tmp;
+                    constexpr int rem = ((row + 1) * W) % TB;
+                    tmp = lane_shr_keep<T, W - rem, rem>(x);
+                }
+            }
+        });
+    }
+    char* pk = packed + blk * (size_t(128) * W) + j * 16;
+    seq_rows<W>([&](auto kc) {
+        constexpr int k = decltype(kc)::value;
+        store_slice<T>(pk + k * 128, outw[k]);
     });
 }
 

@@ -255,10 +255,18 @@ filter_u8_slice_kernel(const char* __restrict__ packed, unsigned char* __restric
         }
         uint32_t bits = 0;
         if constexpr (FilterPred<T, W>::SWAR_FIELD) {
+            // pass bits at 7, 15, 23, 31 of each register.  u * 0x00204081 moves them to bits 28..31 (the partial products
+            // land on distinct positions, the unwanted ones at <= 23 or beyond bit 31: no carries), so a register's nibble
+            // needs no shift-and-mask before the multiply and no mask after it; the four nibbles are chained with
+            // acc = (acc >> 4) | (p & 0xF0000000): 6 instructions per register instead of ~10 (top_bits_u8 + shift-or).
             constexpr R H = 0x80808080u;
+            uint32_t acc = 0;
 #pragma unroll
-            for (int r = 0; r < 4; ++r) bits |= top_bits_u8((v.r[r] + pred.p0) & (pred.p1 - v.r[r]) & H) << (4 * r);
-            bits = (bits ^ pred.invert) & 0xFFFFu;
+            for (int r = 0; r < 4; ++r) {
+                const uint32_t u = (v.r[r] + pred.p0) & (pred.p1 - v.r[r]) & H;
+                acc = (acc >> 4) | ((u * 0x00204081u) & 0xF0000000u);
+            }
+            bits = ((acc >> 16) ^ pred.invert) & 0xFFFFu;
         } else {
             slice_range_bits<T, 0>(bits, v, pred.p0, pred.p1, pred.p2);
             bits &= ~pred.invert;  // empty range
@@ -267,6 +275,68 @@ filter_u8_slice_kernel(const char* __restrict__ packed, unsigned char* __restric
         cnt += uint32_t(__popc(bits));
     });
     if (counts != nullptr) {
+#pragma unroll
+        for (int d = 4; d >= 1; d >>= 1) cnt += __shfl_xor_sync(0xffffffffu, cnt, d);
+        if (active && j == 0) counts[blk] = cnt;
+    }
+}
+
+// ---------------------------------------------------------------------------------------------------
+// u16 filter, ROW-SLICE mapping (0 < W < 16).  The warp-block filter spends, per u16 block, 12-16 run-time lane funnel
+// shifts (4 instructions each: u16 has no native funnel) to align the four groups' runs, ~3 instructions per register to
+// extract, and 5 per register to move two pass bits into place: issue-bound at 0.39-0.72 of the HBM roofline (W = 4..13,
+// profiles/opbench_select_r02_staged_v1.txt).  With 8 threads per block a thread owns the 16-byte column slice of ALL 16
+// rows: every shift is a compile-time constant again (extract_row<W, row>, as in the reference's seq_t! unrolling,
+// src/lib.rs:41-47), nothing crosses threads, and the pass bits of a row's four registers are merged by a shift-or chain
+//     acc = (acc >> 2) | (t1 & t2 & H)        ->  lanes 0,2,4,6 at bits 9,11,13,15; lanes 1,3,5,7 at bits 25,27,29,31
+// so a row's 8 predicate bits — one whole byte of the bitmap, index(r, 8j) / 8 = FL_ORDER[r/8]*2 + (r%8)*16 + j — cost
+// 4 x (2 IADD + LOP3 + SHF + LOP3) + 4 instructions instead of 4 x 10.
+// ---------------------------------------------------------------------------------------------------
+template <int W>
+__global__ void __launch_bounds__(kThreads)
+filter_u16_slice_kernel(const char* __restrict__ packed, unsigned char* __restrict__ bitmap, uint32_t* __restrict__ counts,
+                        size_t n_blocks, const uint16_t* __restrict__ refs, uint16_t ref_scalar, uint16_t lo, uint16_t hi) {
+    using T = uint16_t;
+    using R = uint32_t;
+    static_assert(W > 0 && W < 16, "row-slice u16 filter: widths with a free top bit per lane");
+    constexpr int TB = 16;
+    const size_t tid = size_t(blockIdx.x) * kThreads + threadIdx.x;
+    const size_t blk_raw = tid / kSlicesPerBlock;
+    const int j = int(tid % kSlicesPerBlock);
+    const bool active = blk_raw < n_blocks;  // whole 8-thread groups are active or not
+    const size_t blk = active ? blk_raw : 0;
+    const FilterPred<T, W> pred(refs ? refs[blk] : ref_scalar, lo, hi);  // SWAR_FIELD: p0 = splat(H - A), p1 = splat(H | B)
+    const char* pk = packed + blk * (size_t(128) * W) + j * 16;
+    constexpr int D = (FLB_PREFETCH < W) ? FLB_PREFETCH : W;
+    Slice<T> w[W];
+    seq_rows<D>([&](auto kc) {
+        constexpr int k = decltype(kc)::value;
+        w[k] = load_slice<T>(pk + k * 128);
+    });
+    constexpr R H = 0x80008000u;
+    unsigned char* bm = bitmap + blk * 128 + j;
+    uint32_t words[4] = {0u, 0u, 0u, 0u};  // the thread's 16 row bytes, for the popcount
+    seq_rows<TB>([&](auto rc) {
+        constexpr int row = decltype(rc)::value;
+        constexpr int curr = (row * W) / TB;  // macros.rs:144
+        constexpr bool first_of_word = (row == 0) || (((row - 1) * W) / TB != curr);
+        if constexpr (first_of_word && curr > 0 && curr + D - 1 < W) w[curr + D - 1] = load_slice<T>(pk + (curr + D - 1) * 128);
+        constexpr int nxt = (curr + 1 < W) ? curr + 1 : curr;  // only read when the field straddles (macros.rs:156)
+        const Slice<T> v = extract_row<T, W, row>(w[curr], w[nxt]);
+        uint32_t acc = 0;
+#pragma unroll
+        for (int r = 0; r < 4; ++r) {
+            const uint32_t u = (v.r[r] + pred.p0) & (pred.p1 - v.r[r]) & H;  // top bit of each lane: A <= v <= B
+            acc = (r == 0) ? u : ((acc >> 2) | u);
+        }
+        uint32_t byte = ((acc >> 9) & 0x55u) | ((acc >> 24) & 0xAAu);
+        byte = (byte ^ pred.invert) & 0xFFu;
+        constexpr int off = fl_order(row / 8) * 2 + (row % 8) * 16;  // byte of index(row, 8j) in the block bitmap, minus j
+        if (active) bm[off] = (unsigned char)byte;
+        words[row / 4] |= byte << (8 * (row % 4));
+    });
+    if (counts != nullptr) {
+        uint32_t cnt = uint32_t(__popc(words[0]) + __popc(words[1]) + __popc(words[2]) + __popc(words[3]));
 #pragma unroll
         for (int d = 4; d >= 1; d >>= 1) cnt += __shfl_xor_sync(0xffffffffu, cnt, d);
         if (active && j == 0) counts[blk] = cnt;
@@ -432,17 +502,15 @@ select_warp_kernel(const char* __restrict__ packed, const unsigned char* __restr
     }
 #pragma unroll
     for (int i = 0; i < RPG; ++i) {
-        const int bit0 = c0[i / 8] + (i % 8) * 128;
-        const uint2 e = tile[bit0 >> 5];
+        const uint2 e = (tile + (c0[i / 8] >> 5))[4 * (i % 8)];  // word (c0 + (i%8)*128) / 32: one base, immediate offsets
         const int sh = c0[i / 8] & 31;
         const uint32_t bits = (e.x >> sh) & ((BPT == 32) ? 0xffffffffu : ((1u << BPT) - 1u));
         if (bits == 0) continue;  // nothing selected in this thread's slice of the row
         T* sp = stage + (e.y + uint32_t(__popc(e.x & ((1u << sh) - 1u))));  // rank of the slice's first selected value
-        const Slice<T> val = slice_add<T>(v[i], rs);  // ffor.rs:47
 #pragma unroll
         for (int k = 0; k < BPT; ++k) {
             if (bits & (1u << k)) {  // predicated STS + predicated pointer bump
-                *sp = slice_lane<T>(val, k);
+                *sp = slice_lane<T>(v[i], k);
                 ++sp;
             }
         }
@@ -455,12 +523,13 @@ select_warp_kernel(const char* __restrict__ packed, const unsigned char* __restr
     const uint32_t nvec = (end + EPV - 1) / EPV;
     for (uint32_t x = lane; x < nvec; x += 32) {
         const uint32_t lo = x * EPV;
-        if (lo >= mis && lo + EPV <= end) {
-            stg128_stream(gbase + lo, *reinterpret_cast<const uint4*>(sbase + lo));
+        if (lo >= mis && lo + EPV <= end) {  // the FoR reference is added here, on the selected values only (ffor.rs:47)
+            const Slice<T> val = slice_add<T>(to_slice<T>(*reinterpret_cast<const uint4*>(sbase + lo)), rs);
+            stg128_stream(gbase + lo, from_slice<T>(val));
         } else {
 #pragma unroll
             for (int e = 0; e < EPV; ++e)
-                if (lo + e >= mis && lo + e < end) gbase[lo + e] = sbase[lo + e];
+                if (lo + e >= mis && lo + e < end) gbase[lo + e] = T(sbase[lo + e] + ref);
         }
     }
 }

@@ -14,6 +14,7 @@
 #include <cstdint>
 #include <stdexcept>
 #include <string>
+#include <vector>
 
 #include "fastlanes_b200.h"
 
@@ -47,6 +48,12 @@ template <class T> struct Abi;
         static fl_status delta_filter(unsigned w, size_t n, const T* i, const T* b, T lo, T hi, uint8_t* bm, uint32_t* c) { return fl_host_undelta_pack_filter_##SFX(w, n, i, b, lo, hi, bm, c); } \
         static fl_status transpose(size_t n, const T* i, T* o) { return fl_host_transpose_##SFX(n, i, o); }     \
         static fl_status untranspose(size_t n, const T* i, T* o) { return fl_host_untranspose_##SFX(n, i, o); } \
+        static fl_status ctx_pack(fl_ctx* c, unsigned w, size_t n, const T* i, T* o) { return fl_ctx_host_pack_##SFX(c, w, n, i, o); } \
+        static fl_status ctx_unpack(fl_ctx* c, unsigned w, size_t n, const T* i, T* o) { return fl_ctx_host_unpack_##SFX(c, w, n, i, o); } \
+        static fl_status ctx_for_pack(fl_ctx* c, unsigned w, size_t n, const T* i, T r, T* o) { return fl_ctx_host_for_pack_##SFX(c, w, n, i, r, o); } \
+        static fl_status ctx_unfor_pack(fl_ctx* c, unsigned w, size_t n, const T* i, T r, T* o) { return fl_ctx_host_unfor_pack_##SFX(c, w, n, i, r, o); } \
+        static fl_status ctx_undelta_pack(fl_ctx* c, unsigned w, size_t n, const T* i, const T* b, T* o) { return fl_ctx_host_undelta_pack_##SFX(c, w, n, i, b, o); } \
+        static fl_status ctx_filter(fl_ctx* c, unsigned w, size_t n, const T* i, T r, T lo, T hi, uint8_t* bm, uint32_t* cn) { return fl_ctx_host_unpack_filter_##SFX(c, w, n, i, r, lo, hi, bm, cn); } \
     };
 FLB_ABI(uint8_t, u8)
 FLB_ABI(uint16_t, u16)
@@ -172,5 +179,62 @@ struct Transpose {
     }
 };
 constexpr std::size_t transpose(std::size_t idx) { return (idx % 16) * 64 + FL_ORDER[(idx / 16) % 8] * 8 + idx / 128; }
+
+// Multi-GPU in one process (fl_ctx, include/fastlanes_b200.h): batched forms of the runtime-width family
+// (src/bitpacking.rs:109-129) over whole columns, contiguous block shards on the context's devices.
+class Context {
+  public:
+    explicit Context(const std::vector<int>& devices = {}) {
+        detail::check(fl_ctx_create(devices.empty() ? nullptr : devices.data(), int(devices.size()), &ctx_), "fl_ctx_create");
+    }
+    ~Context() { fl_ctx_destroy(ctx_); }
+    Context(const Context&) = delete;
+    Context& operator=(const Context&) = delete;
+    int device_count() const { return fl_ctx_device_count(ctx_); }
+    std::pair<std::size_t, std::size_t> block_range(std::size_t n_blocks, int i) const {
+        std::size_t a = 0, b = 0;
+        detail::check(fl_ctx_block_range(ctx_, n_blocks, i, &a, &b), "fl_ctx_block_range");
+        return {a, b};
+    }
+    // slices hold whole blocks: unpacked n*1024 elements, packed n*1024*W/T (the reference's debug_asserts, :78-80,:111-113)
+    template <class T>
+    void unchecked_pack(std::size_t width, const std::vector<T>& input, std::vector<T>& output) {
+        const std::size_t n = blocks_of<T>(input, output, width);
+        detail::check(detail::Abi<T>::ctx_pack(ctx_, unsigned(width), n, input.data(), output.data()), "ctx pack");
+    }
+    template <class T>
+    void unchecked_unpack(std::size_t width, const std::vector<T>& input, std::vector<T>& output) {
+        const std::size_t n = blocks_of<T>(output, input, width);
+        detail::check(detail::Abi<T>::ctx_unpack(ctx_, unsigned(width), n, input.data(), output.data()), "ctx unpack");
+    }
+    template <class T>
+    void for_pack(std::size_t width, const std::vector<T>& input, T reference, std::vector<T>& output) {
+        const std::size_t n = blocks_of<T>(input, output, width);
+        detail::check(detail::Abi<T>::ctx_for_pack(ctx_, unsigned(width), n, input.data(), reference, output.data()), "ctx for_pack");
+    }
+    template <class T>
+    void unfor_pack(std::size_t width, const std::vector<T>& input, T reference, std::vector<T>& output) {
+        const std::size_t n = blocks_of<T>(output, input, width);
+        detail::check(detail::Abi<T>::ctx_unfor_pack(ctx_, unsigned(width), n, input.data(), reference, output.data()), "ctx unfor_pack");
+    }
+    template <class T>
+    void undelta_pack(std::size_t width, const std::vector<T>& input, const std::vector<T>& base, std::vector<T>& output) {
+        const std::size_t n = blocks_of<T>(output, input, width);
+        if (base.size() != n * (1024 / (sizeof(T) * 8))) throw Panic(FL_ERR_LEN, "Base buffer must hold LANES elements per block");
+        detail::check(detail::Abi<T>::ctx_undelta_pack(ctx_, unsigned(width), n, input.data(), base.data(), output.data()), "ctx undelta_pack");
+    }
+    fl_ctx* raw() { return ctx_; }
+
+  private:
+    template <class T>
+    static std::size_t blocks_of(const std::vector<T>& unpacked, const std::vector<T>& packed, std::size_t width) {
+        if (unpacked.size() % 1024) throw Panic(FL_ERR_LEN, "unpacked buffer must be a whole number of 1024-element blocks");
+        const std::size_t n = unpacked.size() / 1024;
+        if (width <= sizeof(T) * 8 && packed.size() != n * 1024 * width / (sizeof(T) * 8))
+            throw Panic(FL_ERR_LEN, "packed buffer must be of size n * 1024 * W / T");
+        return n;
+    }
+    fl_ctx* ctx_ = nullptr;
+};
 
 }  // namespace fastlanes

@@ -3,9 +3,11 @@
 //   test_round_trip_*   src/bitpacking.rs:273-315      test_unchecked_pack  :249-256
 //   test_unpack_single  src/bitpacking.rs:259-271      test_delta           src/delta.rs:81-107
 //   test_ffor           src/ffor.rs:67-88              README example       README.md:14-47
+#include <algorithm>
 #include <cstdio>
 #include <cstdlib>
 #include <utility>
+#include <vector>
 
 #include "fastlanes_b200.hpp"
 
@@ -126,6 +128,34 @@ int main() {
         Packed<uint16_t, 3> packed{};
         bool threw = false;
         try { (void)BitPacking<uint16_t>::unpack_single<3>(packed, 1024); } catch (const Panic& p) { threw = p.status == FL_ERR_INDEX; }
+        EXPECT(threw);
+    }
+    {   // context family: a whole column sharded over the devices (device 0 listed twice on a 1-GPU box: two shard
+        // workers), against the single-block trait calls on every block; round trip through pack
+        constexpr std::size_t W = 11, N = 37;
+        std::vector<int> devs = fl_device_count() >= 2 ? std::vector<int>{} : std::vector<int>{0, 0};
+        Context ctx(devs);
+        EXPECT(ctx.device_count() >= 2);
+        EXPECT(ctx.block_range(N, 0).first == 0 && ctx.block_range(N, ctx.device_count() - 1).second == N);
+        std::vector<uint32_t> values(N * 1024), packed(N * 32 * W), decoded(N * 1024), base(N * 32, 7u), dd(N * 1024);
+        for (std::size_t i = 0; i < values.size(); ++i) values[i] = uint32_t((i * 2654435761u) >> 7) & ((1u << W) - 1);
+        ctx.unchecked_pack<uint32_t>(W, values, packed);
+        ctx.unchecked_unpack<uint32_t>(W, packed, decoded);
+        EXPECT(decoded == values);
+        ctx.undelta_pack<uint32_t>(W, packed, base, dd);
+        for (std::size_t b = 0; b < N; b += 9) {
+            std::array<uint32_t, 1024> one{}, ud{};
+            Packed<uint32_t, W> pk{};
+            Delta<uint32_t>::Base bs{};
+            bs.fill(7u);
+            std::copy(values.begin() + b * 1024, values.begin() + (b + 1) * 1024, one.begin());
+            BitPacking<uint32_t>::pack<W>(one, pk);
+            EXPECT(std::equal(pk.begin(), pk.end(), packed.begin() + b * 32 * W));
+            Delta<uint32_t>::undelta_pack<W>(pk, bs, ud);
+            EXPECT(std::equal(ud.begin(), ud.end(), dd.begin() + b * 1024));
+        }
+        bool threw = false;
+        try { std::vector<uint32_t> bad(5); ctx.unchecked_unpack<uint32_t>(W, bad, decoded); } catch (const Panic& p) { threw = p.status == FL_ERR_LEN; }
         EXPECT(threw);
     }
     std::printf(g_fail ? "FAILED (%d)\n" : "ALL OK\n", g_fail);

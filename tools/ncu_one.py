@@ -22,7 +22,7 @@ def main():
     for t in (unp, pk):
         v = t.view(torch.int32) if t.numel() * t.element_size() % 4 == 0 else t
         v.random_(-(1 << 31), (1 << 31) - 1) if v.dtype == torch.int32 else v.random_(0, 255)
-    base = torch.zeros(n * (1024 // tb), dtype=TDT[tb], device="cuda")
+    base = torch.zeros(max(n * (1024 // tb), n), dtype=TDT[tb], device="cuda")
     bm = torch.empty(n * 128, dtype=torch.uint8, device="cuda")
     cnt = torch.empty(n, dtype=torch.int32, device="cuda")
     sp = torch.cuda.current_stream().cuda_stream
@@ -34,6 +34,8 @@ def main():
         "undelta_pack": lambda: _lib.fn("fl_undelta_pack", tb)(w, n, P, B, U, sp),
         "undelta_pack_untranspose": lambda: _lib.fn("fl_undelta_pack_untranspose", tb)(w, n, P, B, U, sp),
         "transpose_delta_pack": lambda: _lib.fn("fl_transpose_delta_pack", tb)(w, n, U, B, P, sp),
+        "for_pack_auto": lambda: _lib.fn("fl_for_pack_auto", tb)(w, n, U, B, None, P, sp),
+        "for_pack": lambda: _lib.fn("fl_for_pack", tb)(w, n, U, 12345 % (1 << tb), P, sp),
         "unpack_filter": lambda: _lib.fn("fl_unpack_filter", tb)(w, n, P, None, 0, m // 4, m // 2, bm.data_ptr(), cnt.data_ptr(), sp),
     }
     if op == "unpack_select":  # value-independent bitmap, ~25 % selected, + the exclusive prefix of the block counts
