@@ -16,10 +16,10 @@
 #define FLB_U8_ORIG_DEFAULT_SLICE 1  // measured: 6.5-7.1 TB/s vs 4.6-6.4 (profiles/opbench_u8orig_r01.txt)
 #endif
 #ifndef FLB_U16_ORIG_SLICE_W
-#define FLB_U16_ORIG_SLICE_W 16  // widths up to this have the row-slice instantiation of the u16 fused original-order chains (A/B at every width)
+#define FLB_U16_ORIG_SLICE_W 1  // widths up to this use the row-slice kernel for the u16 fused ENCODE chain (measured: faster at W = 1 only)
 #endif
 #ifndef FLB_U16_ORIG_DEFAULT_SLICE
-#define FLB_U16_ORIG_DEFAULT_SLICE 0
+#define FLB_U16_ORIG_DEFAULT_SLICE 1
 #endif
 #ifndef FLB_U8_DELTA_W8_DEFAULT_SLICE
 #define FLB_U8_DELTA_W8_DEFAULT_SLICE 1  // measured: 1375 vs 1408 us per 2^22 blocks (profiles/opbench_u8_delta_w8_r02.txt)
@@ -27,8 +27,11 @@
 #ifndef FLB_ORIG_OCC_W
 #define FLB_ORIG_OCC_W 4  // widths up to this have the extra-occupancy instantiation of the fused original-order decode
 #endif
+#ifndef FLB_U16_DELTA_OCC_DEFAULT
+#define FLB_U16_DELTA_OCC_DEFAULT 1  // measured: W=1 787 -> 734 us per 2^21 blocks (profiles/opbench_u16_delta_occ_r02.txt)
+#endif
 #ifndef FLB_ORIG_OCC_DEFAULT
-#define FLB_ORIG_OCC_DEFAULT 1
+#define FLB_ORIG_OCC_DEFAULT 2
 #endif
 #ifndef FLB_U16_FILTER_DEFAULT_SLICE
 #define FLB_U16_FILTER_DEFAULT_SLICE 1
@@ -72,7 +75,7 @@ using launch_fn = cudaError_t (*)(const LaunchArgs&);
     return v;
 }
 
-// u16 fused original-order chains at small W: FLB_U16_ORIG=warp|slice (A/B; default = measured best)
+// u16 fused encode chain at W = 1: FLB_U16_ORIG=warp|slice (A/B; default = measured best)
 [[maybe_unused]] static inline bool u16_orig_slice() {
     static const bool v = [] {
         const char* e = std::getenv("FLB_U16_ORIG");
@@ -110,13 +113,6 @@ static cudaError_t do_unpack(const LaunchArgs& a) {
             T(a.ref_scalar), static_cast<const char*>(a.base));
         return cudaGetLastError();
     }
-    if constexpr (sizeof(T) == 2 && OP == UOP_DELTA_ORIG && W <= FLB_U16_ORIG_SLICE_W) {
-        if (u16_orig_slice()) {
-            undelta_orig_u16_slice_kernel<W><<<grid_for(a.n_blocks), kThreads, 0, a.stream>>>(
-                static_cast<const char*>(a.in), static_cast<char*>(a.out), a.n_blocks, static_cast<const char*>(a.base));
-            return cudaGetLastError();
-        }
-    }
     if constexpr (sizeof(T) == 1 && OP == UOP_DELTA_ORIG) {
         if (u8_orig_slice()) {
             undelta_orig_u8_slice_kernel<W><<<grid_for(a.n_blocks), kThreads, 0, a.stream>>>(
@@ -142,7 +138,8 @@ static cudaError_t do_unpack(const LaunchArgs& a) {
         // Small W: the kernel is latency-bound (ncu u32 W=1: 72 registers -> 3 CTAs per SM, 31 % of the warps resident,
         // DRAM 71 %, profiles/ncu_r02_kernels.md).  A second instantiation whose launch bound holds the compiler to more
         // resident CTAs (u32: 4 = 64 registers; u64: 3 = the shared-memory limit; u16: 6 = 40 registers) is launched
-        // instead.  Measured (profiles/opbench_orig_occ_r02.txt): u32 W=1 811 -> 702 us, u64 W=1 779 -> 710 us.
+        // instead.  Measured (profiles/opbench_orig_occ_r02.txt): u32 W=1 811 -> 702 us, u64 W=1 779 -> 710 us,
+        // u16 W=1 827 -> 760 us per 4 GiB of output.
         // FLB_ORIG_OCC=0|1|2: off / u32 + u64 / also u16 (A/B; default = measured best).
         static const int occ = [] {
             const char* e = std::getenv("FLB_ORIG_OCC");
@@ -153,6 +150,20 @@ static cudaError_t do_unpack(const LaunchArgs& a) {
             static SmemOptIn opt_in2;
             if (const cudaError_t attr = opt_in2.ensure(unpack_warp_kernel<T, W, OP, kTma, false, kMinB>, smem); attr != cudaSuccess) return attr;
             unpack_warp_kernel<T, W, OP, kTma, false, kMinB><<<grid, kThreads, smem, a.stream>>>(
+                static_cast<const char*>(a.in), static_cast<char*>(a.out), a.n_blocks, static_cast<const T*>(a.refs),
+                T(a.ref_scalar), static_cast<const char*>(a.base));
+            return cudaGetLastError();
+        }
+    }
+    if constexpr (OP == UOP_DELTA && sizeof(T) == 2 && W <= FLB_ORIG_OCC_W) {
+        // u16 fused delta at small W (ncu W=1: 48 registers, 51 % of the warps resident, issue 57 %, DRAM 73 %): the same
+        // occupancy lever, 6 CTAs per SM = 40 registers.  FLB_U16_DELTA_OCC=0|1 (A/B; default = measured best).
+        static const bool occ = [] {
+            const char* e = std::getenv("FLB_U16_DELTA_OCC");
+            return e ? e[0] == '1' : FLB_U16_DELTA_OCC_DEFAULT != 0;
+        }();
+        if (occ) {
+            unpack_warp_kernel<T, W, OP, kTma, false, 6><<<grid, kThreads, smem, a.stream>>>(
                 static_cast<const char*>(a.in), static_cast<char*>(a.out), a.n_blocks, static_cast<const T*>(a.refs),
                 T(a.ref_scalar), static_cast<const char*>(a.base));
             return cudaGetLastError();

@@ -1164,65 +1164,17 @@ orig_delta_pack_u8_slice_kernel(const char* __restrict__ in, char* __restrict__ 
 }
 
 // ---------------------------------------------------------------------------------------------------
-// u16 fused original-order chains, ROW-SLICE layout, for SMALL W (round 2).  In the warp-block kernel a u16 block is
-// 2 KiB of output for a whole warp: at W <= 4 the fixed per-warp work (shuffle scan, 8 STS.64 + 4 LDS.128 through the
-// shared tile, MIO queue) leaves it latency-bound at 0.88-0.93 of the roofline (ncu: long_scoreboard + mio_throttle,
-// profiles/ncu_r02_kernels.md).  Same idea as the u8 kernels above: thread j of an 8-thread group owns lanes 8j..8j+7
-// for ALL 16 rows, so the delta chain is a register chain and, for every lane l, the 16 rows are the 16 CONSECUTIVE
-// originals start(l) .. start(l)+15 (src/transpose.rs:29-36 composed with src/macros.rs:20-24) = 32 contiguous bytes at
-//     2*start(l) = 128*(8*(j&1) + k) + 16*FL_ORDER[j>>1]          (l = 8j + k)
-// i.e. two 16-byte global accesses per lane, assembled from the row-major SWAR registers by PRMT.  Registers are
-// processed one SWAR register (two lanes) at a time to keep the live set at 16 rows.  No shared memory, no shuffles.
+// u16 fused ENCODE chain, ROW-SLICE layout, W = 1 (round 2).  Same idea as the u8 kernels above: thread j of an 8-thread
+// group owns lanes 8j..8j+7 for ALL 16 rows, so the delta chain is a register chain and, for every lane l, the 16 rows
+// are the 16 CONSECUTIVE originals start(l) .. start(l)+15 (src/transpose.rs:29-36 composed with src/macros.rs:20-24) =
+// 32 contiguous bytes at 2*start(l) = 128*(8*(j&1) + k) + 16*FL_ORDER[j>>1] (l = 8j + k): two 16-byte loads per lane,
+// re-assembled into row-major SWAR registers by PRMT, one SWAR register (two lanes) at a time.  No shared memory, no
+// shuffles.  Measured (profiles/opbench_u16_orig_slice_r02.txt): transpose_delta_pack u16 W=1 6.06 -> 7.09 TB/s, but
+// slower than the warp-block kernel from W = 2 on (the packed stores of 8 threads are 16-byte pieces of different
+// rows), so it is used at W = 1 only.  The mirror-image DECODE kernel (two 16-byte stores per lane at a 32-byte stride
+// across the group) reached only 2.4 TB/s — half-sector writes — and was dropped; the decode keeps the warp-block
+// kernel with the extra-occupancy instantiation (FLB_ORIG_OCC).
 // ---------------------------------------------------------------------------------------------------
-template <int W>
-__global__ void __launch_bounds__(kThreads)
-undelta_orig_u16_slice_kernel(const char* __restrict__ packed, char* __restrict__ out, size_t n_blocks,
-                              const char* __restrict__ base) {
-    using T = uint16_t;
-    using R = uint32_t;
-    constexpr int TB = 16;
-    const size_t tid = size_t(blockIdx.x) * kThreads + threadIdx.x;
-    const size_t blk = tid / kSlicesPerBlock;
-    const int j = int(tid % kSlicesPerBlock);
-    if (blk >= n_blocks) return;
-    const Slice<T> b0 = load_slice<T>(base + blk * 128 + j * 16);  // delta.rs:50
-    const char* pk = packed + blk * (size_t(128) * W) + j * 16;
-    Slice<T> w[W > 0 ? W : 1];
-    seq_rows<W>([&](auto kc) {
-        constexpr int k = decltype(kc)::value;
-        w[k] = load_slice<T>(pk + k * 128);
-    });
-    char* ob = out + blk * 2048 + 1024 * (j & 1) + 16 * fl_order_rt(j >> 1);
-#pragma unroll
-    for (int r = 0; r < 4; ++r) {
-        R prev = b0.r[r];
-        R v[TB];
-        seq_rows<TB>([&](auto rc) {
-            constexpr int row = decltype(rc)::value;
-            R x;
-            if constexpr (W == 0) x = 0;                 // macros.rs:118-125
-            else if constexpr (W == TB) x = w[row].r[r];  // macros.rs:126-132
-            else {
-                constexpr int curr = (row * W) / TB;
-                constexpr int nxt = (curr + 1 < W) ? curr + 1 : curr;
-                x = extract_field<T, W, row>(w[curr].r[r], w[nxt].r[r]);
-            }
-            prev = lane_add<T>(prev, x);  // delta.rs:58-60
-            v[row] = prev;
-        });
-#pragma unroll
-        for (int h = 0; h < 2; ++h) {  // lane k = 2r + h: its 16 rows = 8 words of two consecutive originals each
-            const uint32_t sel = h ? 0x7632u : 0x5410u;
-            uint32_t m[8];
-#pragma unroll
-            for (int i = 0; i < 8; ++i) m[i] = __byte_perm(v[2 * i], v[2 * i + 1], sel);
-            char* o = ob + 128 * (2 * r + h);
-            stg128_stream(o, make_uint4(m[0], m[1], m[2], m[3]));
-            stg128_stream(o + 16, make_uint4(m[4], m[5], m[6], m[7]));
-        }
-    }
-}
-
 // pack::<W>(delta(transpose(in), base)) for u16 at small W  (src/transpose.rs:11-15, src/delta.rs:24-33, src/macros.rs:35-97)
 template <int W>
 __global__ void __launch_bounds__(kThreads)
