@@ -449,6 +449,54 @@ def ops_table(D: Dev, peak):
             "note": "algorithmic GB/s (SURVEY.md §8d byte formulas), 2 GiB unpacked per type, median of 5 launches, widths {1, T/4, T/2+1, T-3, T}"}
 
 
+def scan_table(D: Dev, peak):
+    """The fused scan entry points x element type x 5 widths: fused range filter, delta range filter
+    and select at ~25 % selectivity, as algorithmic GB/s and G values/s.  Below W ~ T/2 these are instruction-bound by
+    construction (1024 predicate evaluations or compactions per 128*W bytes), so they are reported next to the bandwidth
+    ops, not folded into min_frac_over_ops."""
+    torch = D.torch
+    TDT = {8: torch.uint8, 16: torch.int16, 32: torch.int32, 64: torch.int64}
+    table = {}
+    for tb in (8, 16, 32, 64):
+        n = (1 << 31) // (128 * tb)  # 2 GiB unpacked per type
+        pk = torch.empty(n * 1024, dtype=TDT[tb], device=D.dev); pk.view(torch.int32).random_(-(1 << 31), (1 << 31) - 1)
+        base = torch.empty(n * (1024 // tb), dtype=TDT[tb], device=D.dev); base.view(torch.int32).random_(-(1 << 31), (1 << 31) - 1)
+        bm = torch.empty(n * 128, dtype=torch.uint8, device=D.dev)
+        cnt = torch.empty(n, dtype=torch.int32, device=D.dev)
+        P, B = pk.data_ptr(), base.data_ptr()
+        full = (1 << tb) - 1
+
+        def put(op, w, bpb, fn):
+            fn()
+            r = rec(D.event_times(fn, 5), n, bpb, peak)
+            table.setdefault(op, {}).setdefault(f"u{tb}", {})[str(w)] = {"GBps": r["GBps"], "frac": r["frac"], "Gvalues": r["Gints"]}
+
+        widths = sorted({1, tb // 4, tb // 2 + 1, tb - 3, tb})
+        for w in widths:
+            m = (1 << w) - 1
+            put("unpack_filter", w, 128 * w + 128 + 4,
+                lambda: D.call("fl_unpack_filter", tb, w, n, P, None, 0, m // 4, m // 2, bm.data_ptr(), cnt.data_ptr(), D.sp))
+            put("undelta_pack_filter", w, 128 * w + 128 + 128 + 4,
+                lambda: D.call("fl_undelta_pack_filter", tb, w, n, P, B, full // 4, full // 2, bm.data_ptr(), cnt.data_ptr(), D.sp))
+        # select: a value-independent bitmap of density 1/4 and the exclusive prefix of its per-block counts
+        bm.view(torch.int32).random_(-(1 << 31), (1 << 31) - 1)
+        bm2 = bm.clone(); bm2.view(torch.int32).random_(-(1 << 31), (1 << 31) - 1)
+        bm &= bm2
+        del bm2
+        c64 = torch.tensor([bin(i).count("1") for i in range(256)], dtype=torch.int64, device=D.dev)[bm.long()].view(n, 128).sum(1)
+        offs = torch.cumsum(c64, 0) - c64
+        total = int(c64.sum().item())
+        sel = torch.empty(total + 16, dtype=TDT[tb], device=D.dev)
+        for w in widths:
+            put("unpack_select_25pct", w, 128 * w + 128 + 8 + (tb // 8) * total / n,
+                lambda: D.call("fl_unpack_select", tb, w, n, P, None, 7, bm.data_ptr(), offs.data_ptr(), sel.data_ptr(), D.sp))
+        del pk, base, bm, cnt, c64, offs, sel
+        torch.cuda.empty_cache()
+    return {"ops": table,
+            "note": "algorithmic bytes per block: filter 128*W + 132, delta filter 128*W + 260, select 128*W + 136 + sizeof(T) * selected; "
+                    "2 GiB unpacked per type, median of 5 launches; Gvalues = 1024 * blocks / time"}
+
+
 def end_to_end(D: Dev, fl, np, packed, out, n_blocks, e2e_steps, launch):
     """The sweep through the host-buffer C ABI, its copy-only ceiling, and the same sweep as a host-buffer scan."""
     torch, _lib = D.torch, D._lib
@@ -668,6 +716,7 @@ def main():
         if world == 1 and not args.no_ops:
             other["ops"] = ops_table(D, peak)
             other["min_frac_over_ops"] = other["ops"]["min_frac_over_ops"]
+            other["scan_ops"] = scan_table(D, peak)
     roofline["other"] = other
 
     # ---- end to end through the host-buffer C-ABI (page-locked host memory) ------------------------

@@ -376,35 +376,29 @@ static cudaError_t do_filter(const LaunchArgs& a) {
         static_cast<const T*>(a.refs), T(a.ref_scalar), T(a.flo), T(a.fhi));
     return cudaGetLastError();
 }
+// Blocks per warp of the select kernel, from a full-width sweep of NB = 1 / 4 / 8 on one box at 25 % selectivity
+// (profiles/select_sweep_r02.txt).  NB > 1 hides the load latency behind the previous block but holds a second set of
+// packed words in registers: it pays where the run is short (small or 4-aligned W) and for u64, whose 8 KiB staging buffer
+// per warp caps the resident warps anyway; it loses where the unaligned run already needs 40+ registers (u8, u16, u32 W > 16).
+template <class T, int W>
+constexpr int select_nb() {
+    if constexpr (sizeof(T) == 1) return W == 8 ? 8 : 1;
+    else if constexpr (sizeof(T) == 2) return (W % 4 == 0 && W < 16) ? 8 : 1;
+    else if constexpr (sizeof(T) == 4) {
+        constexpr uint64_t nb8 = (1ull << 0) | (1ull << 2) | (1ull << 3) | (1ull << 4) | (0x1FFull << 8) /* 8..16 */ | (1ull << 20) |
+                                 (7ull << 25) /* 25..27 */ | (1ull << 32);
+        return ((nb8 >> W) & 1) ? 8 : 1;
+    } else return 8;
+}
 template <class T, int W>
 static cudaError_t do_select(const LaunchArgs& a) {
-    const unsigned grid = unsigned((a.n_blocks * 32 + kThreads - 1) / kThreads);
-    // per-warp staging buffer of the compacted values (fl_scan.cuh); u64: 64 KiB per CTA, so the packed block is read
-    // with direct loads there instead of adding the TMA landing buffer on top
-    constexpr bool kTma = sizeof(T) == 2 || sizeof(T) == 4;
+    constexpr int NB = select_nb<T, W>();
+    // per-warp staging buffer of the compacted values (fl_scan.cuh); u64: 64 KiB per CTA
     const size_t smem = size_t(kThreads / 32) * select_stage_bytes<T>();
-    // FLB_SELECT=thread|lane: the thread that decoded a value compacts it (select_warp_kernel) or lane L compacts the 32
-    // values of bitmap word L after an index-order round trip through shared memory (select_lane_kernel); A/B measurement
-    // measured at 25 % selectivity (profiles/opbench_select_r02.txt): lane is faster for u8 (1.82-1.99 vs 2.07-2.53 ms per
-    // 2^22 blocks) and for u64 above W ~ 32 (W=64: 0.97 vs 1.65 ms); thread for u16 / u32 and narrow u64
-    static const int forced = [] {
-        const char* e = std::getenv("FLB_SELECT");
-        if (e && std::strcmp(e, "thread") == 0) return 0;
-        if (e && std::strcmp(e, "lane") == 0) return 1;
-        return -1;
-    }();
-    const bool lane_variant = forced >= 0 ? forced == 1 : (sizeof(T) == 1 || (sizeof(T) == 8 && W > 32));
-    if (lane_variant) {
-        static SmemOptIn opt_in;
-        if (const cudaError_t attr = opt_in.ensure(select_lane_kernel<T, W, kTma>, smem); attr != cudaSuccess) return attr;
-        select_lane_kernel<T, W, kTma><<<grid, kThreads, smem, a.stream>>>(
-            static_cast<const char*>(a.in), static_cast<const unsigned char*>(a.bitmap), a.offsets, static_cast<T*>(a.out),
-            a.n_blocks, static_cast<const T*>(a.refs), T(a.ref_scalar));
-        return cudaGetLastError();
-    }
     static SmemOptIn opt_in;
-    if (const cudaError_t attr = opt_in.ensure(select_warp_kernel<T, W, kTma>, smem); attr != cudaSuccess) return attr;
-    select_warp_kernel<T, W, kTma><<<grid, kThreads, smem, a.stream>>>(
+    if (const cudaError_t attr = opt_in.ensure(select_warp_kernel<T, W, NB>, smem); attr != cudaSuccess) return attr;
+    const size_t warps = (a.n_blocks + NB - 1) / NB;
+    select_warp_kernel<T, W, NB><<<unsigned((warps * 32 + kThreads - 1) / kThreads), kThreads, smem, a.stream>>>(
         static_cast<const char*>(a.in), static_cast<const unsigned char*>(a.bitmap), a.offsets, static_cast<T*>(a.out),
         a.n_blocks, static_cast<const T*>(a.refs), T(a.ref_scalar));
     return cudaGetLastError();

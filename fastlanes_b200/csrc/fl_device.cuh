@@ -265,6 +265,7 @@ __device__ __forceinline__ typename Lay<T>::R extract_field(typename Lay<T>::R c
         // macros.rs:164 (and :154 with remaining_bits == 0)
         if constexpr (Lay<T>::LPR == 1 && shift + W == TB) return cur >> shift;
         else if constexpr (shift == 0) return cur & MW;
+        else if constexpr (sizeof(T) == 4 && W == 8) return __byte_perm(cur, 0u, 0x4440u + shift / 8);  // one PRMT, not SHF + LOP3
         else return (cur >> shift) & MW;
     } else {
         // macros.rs:149-161: low current_bits from cur, the remaining bits from the next word-row

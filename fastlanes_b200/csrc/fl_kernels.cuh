@@ -145,7 +145,7 @@ struct WarpLay {
     static constexpr int RPG = TB / 4;  // rows per group
     // rank (position in row order) of group g.  u32/u64: {0,2,1,3} makes the 4 groups' rows adjacent in memory.
     __device__ static __forceinline__ int rank_of_group(int g) {
-        if constexpr (sizeof(T) >= 4) return (g == 1) ? 2 : (g == 2 ? 1 : g);
+        if constexpr (sizeof(T) >= 4) return ((g << 1) & 2) | (g >> 1);  // swaps 1 and 2 (g < 4) without the branchy select chain
         else return g;
     }
     __device__ static __forceinline__ int group_of_rank(int q) { return rank_of_group(q); }  // involution / identity

@@ -427,220 +427,208 @@ delta_filter_warp_kernel(const char* __restrict__ packed, const char* __restrict
     }
 }
 
-// lane k (0 .. 16/sizeof(T) - 1) of a 16-byte slice
-template <class T>
-__device__ __forceinline__ T slice_lane(const Slice<T>& s, int k) {
-    if constexpr (sizeof(T) >= 4) return T(s.r[k]);
-    else if constexpr (sizeof(T) == 2) return T(s.r[k >> 1] >> (16 * (k & 1)));
-    else return T(s.r[k >> 2] >> (8 * (k & 3)));
-}
-
 // ---------------------------------------------------------------------------------------------------
-// select (dense compaction of the values a bitmap selects).  Store side, round 2: the round-1 kernel issued one
-// predicated 1-element st.global per value straight from the decode registers — 1024 scattered stores per block whose
-// partial-sector writes cost 3.0x the algorithmic L2 write traffic (profiles/ncu_s2_r01.md).  Now the selected values
-// are first compacted into a warp-private shared-memory staging buffer (predicated STS at the value's rank, computed
-// as before from the per-word popcount scan), laid out with the SAME 16-byte phase as the destination out + offsets[b],
-// and then drained with full 16-byte coalesced STG.128 — only the (at most two) edge vectors of a block's output run
-// use element stores.  Every output byte is written exactly once, in sector-sized pieces.
+// select (dense compaction of the values a bitmap selects): out[offsets[b] + k] = the k-th selected value of block b.
+// One warp = one block at a time, the thread that decoded a value compacts it.  History of the store side and of the
+// instruction count (profiles/ncu_s2_r01.md, profiles/ncu_r02_kernels.md, profiles/ncu_r02_select.md):
+//   round 1   one predicated 1-element st.global per value straight from the decode registers: partial-sector writes cost
+//             3.0x the algorithmic L2 write traffic.
+//   round 2a  selected values are first compacted into a warp-private shared-memory staging buffer (predicated STS at the
+//             value's rank, from the per-word popcount scan), laid out with the SAME 16-byte phase as the destination
+//             out + offsets[b], and drained with full 16-byte coalesced STG.128; every output byte is written once, in
+//             sector-sized pieces (write traffic 1.0x).  524 issued instructions per u32 block, issue slots 75 % busy.
+//   round 2b  a lane-per-bitmap-word variant (index-order round trip through shared memory) — faster only for u8; deleted.
+//   round 2c  (this kernel) per-row and per-block overheads removed:
+//     * the (bitmap word, prefix) table holds the SHARED BYTE ADDRESS of the word's first output slot, so a row's first
+//       store address is one multiply-add on the popcount of the lower bits (was: add, add, multiply-add);
+//     * the slice's bitmap bits are rotated to positions 1 .. BPT so that one R2P moves them all into predicates;
+//     * no "nothing selected in my slice of this row" branch — at any selectivity worth a dense output it was never
+//       taken by all 32 lanes, so it only cost the test and the reconvergence pair;
+//     * the SWAR types store the low byte / halfword of the shifted register (st.shared.u8 / .u16 truncate): no mask;
+//     * the drain no longer diverges: full 16-byte vectors in one loop, the (at most two) partial edge vectors of the
+//       block's output run by one predicated element store per lane;
+//     * direct 128-bit loads instead of the TMA bulk load (no mbarrier round trip; as in the filter kernels);
+//     * NB consecutive blocks per warp with all global loads of block b + 1 issued before block b is processed: ncu on
+//       the one-block-per-warp version put 29 % of all warp samples on the first use of the bitmap word and the packed
+//       words (two dependent DRAM round trips per warp lifetime).
+//   u32 W = 8 at 25 % selectivity: 615 -> 468 us per 2^20 blocks (0.55 -> 0.75 of the measured HBM peak); 323 issued
+//   instructions per block.
 //   dynamic shared memory: kThreads/32 warps x select_stage_bytes<T>()
 // ---------------------------------------------------------------------------------------------------
 template <class T>
 __host__ __device__ constexpr int select_stage_bytes() { return 1024 * int(sizeof(T)) + 16; }
 
-template <class T, int W, bool TMA>
+template <class T>
+__device__ __forceinline__ void sts_low(uint32_t sa, typename Lay<T>::R x) {
+    if constexpr (sizeof(T) == 1) asm volatile("st.shared.u8 [%0], %1;" ::"r"(sa), "r"(x) : "memory");
+    else if constexpr (sizeof(T) == 2) asm volatile("st.shared.u16 [%0], %1;" ::"r"(sa), "r"(x) : "memory");
+    else if constexpr (sizeof(T) == 4) asm volatile("st.shared.b32 [%0], %1;" ::"r"(sa), "r"(x) : "memory");
+    else asm volatile("st.shared.b64 [%0], %1;" ::"r"(sa), "l"((unsigned long long)x) : "memory");
+}
+// lane k of a 16-byte slice in the low bits of a register (the bits above it are other lanes)
+template <class T>
+__device__ __forceinline__ typename Lay<T>::R slice_lane_low(const Slice<T>& s, int k) {
+    constexpr int LPR = Lay<T>::LPR;
+    return s.r[k / LPR] >> (Lay<T>::TB * (k % LPR));
+}
+
+// number of word-row loads warp_run_from issues for one thread
+template <class T, int W>
+__host__ __device__ constexpr int run_loads() {
+    constexpr int TB = Lay<T>::TB, RPG = TB / 4;
+    return W == 0 ? 0 : (W == TB ? RPG : ((W % 4) == 0 ? run_words<T, W>() : run_words<T, W>() + 1));
+}
+// everything a block's compaction needs from global memory, loaded one block ahead of its use
+template <class T, int W>
+struct SelectLoads {
+    uint32_t mword;  // this lane's word of the block bitmap
+    uint64_t obase;  // offsets[blk]
+    T ref;
+    uint4 raw[run_loads<T, W>() > 0 ? run_loads<T, W>() : 1];  // this thread's slices of the word-rows of its run
+};
+template <class T, int W>
+__device__ __forceinline__ void select_issue_loads(SelectLoads<T, W>& ld, size_t blk, int lane, int q, int j,
+                                                   const char* __restrict__ packed, const unsigned char* __restrict__ bitmap,
+                                                   const uint64_t* __restrict__ offsets, const T* __restrict__ refs, T ref_scalar) {
+    ld.mword = reinterpret_cast<const uint32_t*>(bitmap + blk * 128)[lane];
+    ld.obase = offsets[blk];
+    ld.ref = refs ? refs[blk] : ref_scalar;
+    if constexpr (W > 0) {
+        const char* pk = packed + blk * (size_t(128) * W) + j * 16;
+        int n = 0;
+        Slice<T> unused[run_words<T, W>()];  // the alignment shifts happen at the point of use (dead here)
+        warp_run_from<T, W>([&](unsigned k) -> Slice<T> { ld.raw[n] = ldg128_stream(pk + k * 128); return to_slice<T>(ld.raw[n++]); }, q, unused);
+    }
+}
+
+template <class T, int W, int NB>
 __global__ void __launch_bounds__(kThreads)
 select_warp_kernel(const char* __restrict__ packed, const unsigned char* __restrict__ bitmap,
-                   const uint64_t* __restrict__ offsets, T* __restrict__ out, size_t n_blocks,
-                   const T* __restrict__ refs, T ref_scalar) {
+                    const uint64_t* __restrict__ offsets, T* __restrict__ out, size_t n_blocks,
+                    const T* __restrict__ refs, T ref_scalar) {
     using WL = WarpLay<T>;
     constexpr int TB = Lay<T>::TB;
     constexpr int RPG = WL::RPG;
     constexpr int BPT = 128 / TB;
-    constexpr int EPV = 16 / int(sizeof(T));  // elements per 16-byte vector
-    const size_t blk = (size_t(blockIdx.x) * kThreads + threadIdx.x) >> 5;
-    if (blk >= n_blocks) return;  // warp-uniform
+    constexpr int S = int(sizeof(T));
+    constexpr int EPV = 16 / S;  // elements per 16-byte vector
+    static_assert(NB == 1 || NB % 2 == 0, "the block loop is unrolled by two (ping-pong of the prefetch registers)");
+    const size_t blk0 = ((size_t(blockIdx.x) * kThreads + threadIdx.x) >> 5) * NB;
+    if (blk0 >= n_blocks) return;  // warp-uniform
     const int lane = threadIdx.x & 31;
     const int g = lane >> 3, j = lane & 7;
     const int q = WL::rank_of_group(g);
-    // independent loads first (before the decode's TMA wait)
-    const uint32_t mword = reinterpret_cast<const uint32_t*>(bitmap + blk * 128)[lane];
-    const uint64_t obase = offsets[blk];
-    const T ref = refs ? refs[blk] : ref_scalar;
-    // exclusive prefix of the per-word popcounts: rank of the first bit of word `lane` among the block's set bits
-    const uint32_t cnt = uint32_t(__popc(mword));
-    uint32_t incl = cnt;
-#pragma unroll
-    for (int d = 1; d < 32; d <<= 1) {
-        const uint32_t t = __shfl_up_sync(0xffffffffu, incl, d);
-        if (lane >= d) incl += t;
-    }
-    const uint32_t total = __shfl_sync(0xffffffffu, incl, 31);
-    if (total == 0) return;  // nothing selected in this block: skip the decode
-    __shared__ uint2 sel_tile[kThreads / 32][32];  // (bitmap word, exclusive prefix)
+    __shared__ uint2 sel_tile[kThreads / 32][32];  // (bitmap word, shared byte address of the word's first output slot)
     uint2* tile = sel_tile[threadIdx.x >> 5];
-    tile[lane] = make_uint2(mword, incl - cnt);
-    __syncwarp();
-
-    Slice<T> v[RPG];
-    warp_decode_tile<T, W, TMA, (kThreads / 32) * 256>(packed + blk * (size_t(128) * W), lane, q, j, v);
-    const Slice<T> rs = slice_splat<T>(ref);
-
     extern __shared__ __align__(16) unsigned char select_stage_smem[];
-    T* o = out + obase;
-    const uint32_t mis = uint32_t((reinterpret_cast<uintptr_t>(o) & 15u) / sizeof(T));  // phase of the run inside a 16-byte vector
-    T* stage = reinterpret_cast<T*>(select_stage_smem + (threadIdx.x >> 5) * select_stage_bytes<T>()) + mis;
+    unsigned char* stage = select_stage_smem + (threadIdx.x >> 5) * select_stage_bytes<T>();  // 16-byte aligned
+    const uint32_t stage_sa = smem_addr(stage);
     // Original index of this thread's first lane in local row i: index(q*RPG + i, j*BPT) (macros.rs:20-24).  Rows of one
     // 8-row band share FL_ORDER[r/8], so inside a band bit0 = c0 + (r%8)*128: the bit position inside the 32-bit bitmap
     // word (sh) and the mask of the lower bits are per-thread constants, the word index advances by 4 per row.
     constexpr int BANDS = RPG > 8 ? RPG / 8 : 1;
-    int c0[BANDS];
+    const uint2* trow[BANDS];
+    uint32_t sh[BANDS], lowmask[BANDS];
 #pragma unroll
     for (int bnd = 0; bnd < BANDS; ++bnd) {
         const int r0 = q * RPG + bnd * 8;  // first global row of the band (RPG < 8: of the run)
-        c0[bnd] = scan_fl_order(r0 >> 3) * 16 + (r0 & 7) * 128 + j * BPT;
+        const int c0 = scan_fl_order(r0 >> 3) * 16 + (r0 & 7) * 128 + j * BPT;
+        trow[bnd] = tile + (c0 >> 5);
+        const uint32_t s0 = uint32_t(c0 & 31);
+        sh[bnd] = (s0 + 31u) & 31u;  // rotate right by s0 - 1: the slice's bits land at positions 1 .. BPT (see below)
+        lowmask[bnd] = (1u << s0) - 1u;
     }
+
+    // One block: `cur` was loaded during the previous block (or before the loop); the loads of block blk + 1 are issued
+    // into `nxt` BEFORE this block is processed, so a warp waits for DRAM once per NB blocks, not once (or twice: bitmap,
+    // then packed) per block.  ncu, one block per warp: 29 % of all warp samples sat on the first use of the bitmap word
+    // and of the packed words (profiles/ncu_r02_select.md).
+    auto one_block = [&](size_t blk, bool more, const SelectLoads<T, W>& cur, SelectLoads<T, W>& nxt) {
+        if (more) select_issue_loads<T, W>(nxt, blk + 1, lane, q, j, packed, bitmap, offsets, refs, ref_scalar);
+        const uint32_t mword = cur.mword;
+        // exclusive prefix of the per-word popcounts: rank of the first bit of word `lane` among the block's set bits
+        const uint32_t cnt = uint32_t(__popc(mword));
+        uint32_t incl = cnt;
 #pragma unroll
-    for (int i = 0; i < RPG; ++i) {
-        const uint2 e = (tile + (c0[i / 8] >> 5))[4 * (i % 8)];  // word (c0 + (i%8)*128) / 32: one base, immediate offsets
-        const int sh = c0[i / 8] & 31;
-        const uint32_t bits = (e.x >> sh) & ((BPT == 32) ? 0xffffffffu : ((1u << BPT) - 1u));
-        if (bits == 0) continue;  // nothing selected in this thread's slice of the row
-        T* sp = stage + (e.y + uint32_t(__popc(e.x & ((1u << sh) - 1u))));  // rank of the slice's first selected value
+        for (int d = 1; d < 32; d <<= 1) {
+            const uint32_t t = __shfl_up_sync(0xffffffffu, incl, d);
+            if (lane >= d) incl += t;
+        }
+        const uint32_t total = __shfl_sync(0xffffffffu, incl, 31);
+        // Nothing selected: skip the decode.  The exit also depends on the packed words (`dep`): ptxas sinks loads below an
+        // exit on whose path they are dead — with one block per warp that puts the bitmap and the packed round trips in
+        // series.  Taking the long path with total == 0 is harmless (every store is predicated on a set bit, the drain is
+        // empty), so the extra condition may be anything the compiler cannot fold.
+        uint32_t dep = 0;
 #pragma unroll
-        for (int k = 0; k < BPT; ++k) {
-            if (bits & (1u << k)) {  // predicated STS + predicated pointer bump
-                *sp = slice_lane<T>(v[i], k);
-                ++sp;
+        for (int n = 0; n < run_loads<T, W>(); ++n) dep |= cur.raw[n].x;
+        if (total == 0 && __all_sync(0xffffffffu, dep != 0x5bd1e995u)) return;  // the vote keeps the branch warp-uniform
+        T* o = out + cur.obase;
+        const uint32_t mis = uint32_t((reinterpret_cast<uintptr_t>(o) & 15u) / sizeof(T));  // phase of the run inside a 16-byte vector
+        // (the previous block's table look-ups ended before its pre-drain __syncwarp, and its drain reads end before any lane
+        // passes the __syncwarp below, which is ahead of the first staging store of this block)
+        tile[lane] = make_uint2(mword, stage_sa + (mis + incl - cnt) * uint32_t(S));
+        __syncwarp();
+
+        Slice<T> a[run_words<T, W>()];
+        {
+            int n = 0;
+            warp_run_from<T, W>([&](unsigned) -> Slice<T> { return to_slice<T>(cur.raw[n++]); }, q, a);
+        }
+        Slice<T> v[RPG];
+        warp_extract_rows<T, W>(a, v);
+#pragma unroll
+        for (int i = 0; i < RPG; ++i) {
+            const uint2 e = trow[i / 8][4 * (i % 8)];  // word (c0 + (i%8)*128) / 32: one base, immediate offsets
+            // bit k of the slice at position k + 1: the compiler moves register bits 1.. into predicates with one R2P, but
+            // spends two extra instructions on bit 0 (P0 is its scratch predicate)
+            const uint32_t bits = __funnelshift_r(e.x, e.x, sh[i / 8]);
+            uint32_t sa = e.y + uint32_t(__popc(e.x & lowmask[i / 8])) * uint32_t(S);  // slot of the slice's first selected value
+#pragma unroll
+            for (int k = 0; k < BPT; ++k) {
+                if (bits & (2u << k)) {  // predicated STS + predicated address bump
+                    sts_low<T>(sa, slice_lane_low<T>(v[i], k));
+                    sa += uint32_t(S);
+                }
             }
         }
-    }
-    __syncwarp();
-    // drain: stage[-mis .. ) and o - mis are both 16-byte aligned; vector x covers run elements [x*EPV - mis, ...)
-    const T* sbase = stage - mis;
-    T* gbase = o - mis;
-    const uint32_t end = mis + total;
-    const uint32_t nvec = (end + EPV - 1) / EPV;
-    for (uint32_t x = lane; x < nvec; x += 32) {
-        const uint32_t lo = x * EPV;
-        if (lo >= mis && lo + EPV <= end) {  // the FoR reference is added here, on the selected values only (ffor.rs:47)
-            const Slice<T> val = slice_add<T>(to_slice<T>(*reinterpret_cast<const uint4*>(sbase + lo)), rs);
-            stg128_stream(gbase + lo, from_slice<T>(val));
-        } else {
-#pragma unroll
-            for (int e = 0; e < EPV; ++e)
-                if (lo + e >= mis && lo + e < end) gbase[lo + e] = T(sbase[lo + e] + ref);
+        __syncwarp();
+        // drain: stage and o - mis are both 16-byte aligned; vector x covers run elements [x*EPV - mis, ...); the FoR
+        // reference is added here, on the selected values only (ffor.rs:47)
+        const T ref = cur.ref;
+        const Slice<T> rs = slice_splat<T>(ref);
+        const T* sT = reinterpret_cast<const T*>(stage);
+        T* gbase = o - mis;
+        const uint32_t end = mis + total;
+        const uint32_t vfirst = mis != 0 ? 1u : 0u;  // first vector lying entirely inside the run
+        const uint32_t vlast = end / EPV;            // one past the last such vector
+        unsigned char* gb = reinterpret_cast<unsigned char*>(gbase);
+#pragma unroll 1
+        for (uint32_t off = (vfirst + lane) * 16u; off < vlast * 16u; off += 512u) {
+            const Slice<T> val = slice_add<T>(to_slice<T>(*reinterpret_cast<const uint4*>(stage + off)), rs);
+            stg128_stream(gb + off, from_slice<T>(val));
+        }
+        if (lane < EPV) {
+            const uint32_t eh = uint32_t(lane);  // head: run elements inside vector 0 when the run starts mid-vector
+            if (mis != 0 && eh >= mis && eh < end) gbase[eh] = T(sT[eh] + ref);
+            const uint32_t et = vlast * EPV + uint32_t(lane);  // tail: the elements after the last full vector
+            if (vlast >= vfirst && et < end) gbase[et] = T(sT[et] + ref);
+        }
+    };
+
+    SelectLoads<T, W> ld0, ld1;
+    select_issue_loads<T, W>(ld0, blk0, lane, q, j, packed, bitmap, offsets, refs, ref_scalar);
+    if constexpr (NB == 1) {
+        one_block(blk0, false, ld0, ld1);
+    } else {
+        const size_t blk_end = (n_blocks - blk0 < size_t(NB)) ? n_blocks : blk0 + NB;
+#pragma unroll 1
+        for (size_t blk = blk0; blk < blk_end; blk += 2) {
+            one_block(blk, blk + 1 < blk_end, ld0, ld1);
+            if (blk + 1 >= blk_end) break;
+            one_block(blk + 1, blk + 2 < blk_end, ld1, ld0);
         }
     }
-}
-
-// ---------------------------------------------------------------------------------------------------
-// select, LANE-PER-WORD variant (round 2, second step).  In select_warp_kernel a thread compacts the values it decoded:
-// per value an extraction, the reference add, a predicated STS and a predicated pointer bump, plus per row a shared
-// lookup of (bitmap word, prefix) — ~450 instructions per block, issue-bound (u8: 2.0 ms per 2^22 blocks).  Here the
-// decoded tile is first written to shared memory in INDEX order (= the unpacked block layout, one STS.128 per row,
-// XOR-swizzled per 128-byte line), and then lane L re-reads the 32 consecutive values of bitmap word L — the word and
-// its exclusive prefix are already in L's registers from the popcount scan.  Compaction is then 32 x (predicated STS +
-// predicated bump) per lane with no lookups, the staging buffer is the same shared region (all lanes have their values
-// in registers before the first compacted store), and the reference add moves to the 16-byte drain (SWAR, selected
-// values only).
-// ---------------------------------------------------------------------------------------------------
-// swizzle of the 16-byte chunk index inside 128-byte line `line`: makes the lane-per-word re-read conflict-free
-// (u8: a lane owns 2 chunks, 4 lanes per line; u16: 4 chunks, 2 lanes per line; u32: a whole line; u64: two lines)
-template <class T>
-__device__ __forceinline__ int select_swz(int line) {
-    if constexpr (sizeof(T) == 1) return line & 1;
-    else if constexpr (sizeof(T) == 2) return line & 3;
-    else if constexpr (sizeof(T) == 4) return line & 7;
-    else return (line >> 1) & 7;
-}
-
-template <class T, int W, bool TMA>
-__global__ void __launch_bounds__(kThreads)
-select_lane_kernel(const char* __restrict__ packed, const unsigned char* __restrict__ bitmap,
-                   const uint64_t* __restrict__ offsets, T* __restrict__ out, size_t n_blocks,
-                   const T* __restrict__ refs, T ref_scalar) {
-    using WL = WarpLay<T>;
-    using R = typename Lay<T>::R;
-    constexpr int TB = Lay<T>::TB;
-    constexpr int RPG = WL::RPG;
-    constexpr int S = int(sizeof(T));
-    constexpr int EPV = 16 / S;       // elements per 16-byte vector
-    constexpr int NV = 32 * S / 16;   // 16-byte vectors holding the 32 values of one bitmap word
-    constexpr int LPR = Lay<T>::LPR;  // values per SWAR register
-    const size_t blk = (size_t(blockIdx.x) * kThreads + threadIdx.x) >> 5;
-    if (blk >= n_blocks) return;  // warp-uniform
-    const int lane = threadIdx.x & 31;
-    const int g = lane >> 3, j = lane & 7;
-    const int q = WL::rank_of_group(g);
-    // independent loads first (before the decode's TMA wait)
-    const uint32_t mword = reinterpret_cast<const uint32_t*>(bitmap + blk * 128)[lane];
-    const uint64_t obase = offsets[blk];
-    const T ref = refs ? refs[blk] : ref_scalar;
-    const uint32_t cnt = uint32_t(__popc(mword));
-    uint32_t incl = cnt;
-#pragma unroll
-    for (int d = 1; d < 32; d <<= 1) {
-        const uint32_t t = __shfl_up_sync(0xffffffffu, incl, d);
-        if (lane >= d) incl += t;
-    }
-    const uint32_t total = __shfl_sync(0xffffffffu, incl, 31);
-    if (total == 0) return;  // nothing selected in this block: skip the decode
-
-    Slice<T> v[RPG];
-    warp_decode_tile<T, W, TMA>(packed + blk * (size_t(128) * W), lane, q, j, v);
-
-    extern __shared__ __align__(16) unsigned char select_stage_smem[];
-    unsigned char* buf = select_stage_smem + (threadIdx.x >> 5) * select_stage_bytes<T>();
-    // 1) the decoded tile in index order: row r of the block is 128-byte line index(r, 0) * S / 128 (macros.rs:20-24)
-    seq_rows<RPG>([&](auto ic) {
-        constexpr int i = decltype(ic)::value;
-        const int line = warp_row_offset<T, i>(q) >> 7;
-        *reinterpret_cast<uint4*>(buf + line * 128 + ((j ^ select_swz<T>(line)) << 4)) = from_slice<T>(v[i]);
-    });
-    __syncwarp();
-    // 2) lane L takes the 32 values of bitmap word L: bytes [32*S*L, 32*S*(L+1)) of the tile
-    Slice<T> x[NV];
-#pragma unroll
-    for (int k = 0; k < NV; ++k) {
-        const int a = lane * (32 * S) + k * 16;
-        const int line = a >> 7, c = (a >> 4) & 7;
-        x[k] = to_slice<T>(*reinterpret_cast<const uint4*>(buf + line * 128 + ((c ^ select_swz<T>(line)) << 4)));
-    }
-    __syncwarp();  // every lane holds its values: the region is now the compaction target
-    T* o = out + obase;
-    const uint32_t mis = uint32_t((reinterpret_cast<uintptr_t>(o) & 15u) / sizeof(T));  // phase of the run inside a 16-byte vector
-    T* stage = reinterpret_cast<T*>(buf) + mis;
-    T* sp = stage + (incl - cnt);
-#pragma unroll
-    for (int k = 0; k < NV; ++k) {
-#pragma unroll
-        for (int e = 0; e < EPV; ++e) {
-            if (mword & (1u << (k * EPV + e))) {  // predicated STS + predicated pointer bump
-                *sp = T(x[k].r[e / LPR] >> (TB * (e % LPR)));
-                ++sp;
-            }
-        }
-    }
-    __syncwarp();
-    // 3) drain: stage - mis and o - mis are both 16-byte aligned; the FoR reference is added here (ffor.rs:47)
-    const Slice<T> rs = slice_splat<T>(ref);
-    const T* sbase = stage - mis;
-    T* gbase = o - mis;
-    const uint32_t end = mis + total;
-    const uint32_t nvec = (end + EPV - 1) / EPV;
-    for (uint32_t xv = lane; xv < nvec; xv += 32) {
-        const uint32_t lo = xv * EPV;
-        if (lo >= mis && lo + EPV <= end) {
-            const Slice<T> val = slice_add<T>(to_slice<T>(*reinterpret_cast<const uint4*>(sbase + lo)), rs);
-            stg128_stream(gbase + lo, from_slice<T>(val));
-        } else {
-#pragma unroll
-            for (int e = 0; e < EPV; ++e)
-                if (lo + e >= mis && lo + e < end) gbase[lo + e] = T(sbase[lo + e] + ref);
-        }
-    }
-    (void)sizeof(R);
 }
 
 }  // namespace flb

@@ -100,6 +100,32 @@ def test_select_every_width_device(fl, oracle, tb):
         assert np.all(got[total:] == DT[tb](0x3C if tb == 8 else 0x3C3C)), (tb, w, "wrote past the selected count")
 
 
+@pytest.mark.parametrize("tb", [8, 16, 32, 64])
+def test_select_per_block_references_ragged(fl, oracle, tb):
+    """Per-block FoR references (added on the selected values only, src/ffor.rs:47) on a batch that is ragged against the
+    blocks-per-warp loop of the kernel (1 and 8 per warp depending on type / width) and whose output runs start at every
+    phase of a 16-byte vector; sparse bitmaps with many empty blocks exercise the early exit inside that loop."""
+    import torch
+
+    rng = np.random.default_rng(1300 + tb)
+    n = 1031
+    for w in sorted({0, 1, 4, tb // 4, tb // 2 + 1, tb - 3, tb}):
+        packed = rand_bytes(rng, n * 128 * w, tb)
+        refs = rand_bytes(rng, n * (tb // 8), tb)
+        values = oracle.unfor_pack(packed, refs, w, n_blocks=n)
+        sel = rng.random(n * 1024) < np.repeat(rng.choice([0.0, 0.0, 0.001, 0.25, 1.0], n), 1024)
+        bitmap = np.packbits(sel, bitorder="little")
+        counts = sel.reshape(n, 1024).sum(1).astype(np.int64)
+        offsets = np.concatenate([[0], np.cumsum(counts)[:-1]]).astype(np.int64)
+        total = int(counts.sum())
+        out = dev_empty(total + 16, tb)
+        out.fill_(0x3C if tb == 8 else 0x3C3C)
+        fl.Scan.select(w, to_dev(packed), to_dev(refs), torch.from_numpy(bitmap).cuda(), torch.from_numpy(offsets).cuda(), out)
+        got = to_host(out, tb)
+        assert np.array_equal(got[:total], values[sel]), (tb, w)
+        assert np.all(got[total:] == DT[tb](0x3C if tb == 8 else 0x3C3C)), (tb, w, "wrote past the selected count")
+
+
 def test_filter_then_select_pipeline_u32(fl, oracle):
     """filter -> exclusive scan of the counts (torch.cumsum, plumbing) -> select == values[lo <= values <= hi]."""
     import torch
