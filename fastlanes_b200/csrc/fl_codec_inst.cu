@@ -371,6 +371,17 @@ static cudaError_t do_filter(const LaunchArgs& a) {
     // Direct 128-bit loads, not the TMA bulk load: the filter reads little per block and is ALU-bound below W ~ 3T/4,
     // where the mbarrier round trip costs 10-15 % (u32 W=8: 300 vs 346 us; equal at W >= 29 —
     // profiles/opbench_filter_tma_r01.txt).
+    // One-block-ahead loads (fl_scan.cuh, RunLoads) with 8 blocks per warp where they measured faster: u64 W = 16 242 -> 195 us,
+    // u32 W = 1 / 8 203 -> 189 / 211 -> 205 us per 4 GiB of values; u64 W = 33 / 61 lose 20-40 % to the second register set,
+    // everything else is within 1 % (profiles/opbench_filter_pipe_r02.txt).
+    constexpr bool kPipe = kNB > 1 && ((sizeof(T) == 8 && W <= 16) || (sizeof(T) == 4 && W <= 8));
+    if constexpr (kPipe) {
+        const size_t warps8 = (a.n_blocks + 7) / 8;
+        filter_warp_kernel<T, W, false, 8, true><<<unsigned((warps8 * 32 + kThreads - 1) / kThreads), kThreads, 0, a.stream>>>(
+            static_cast<const char*>(a.in), static_cast<unsigned char*>(a.out), a.counts, a.n_blocks,
+            static_cast<const T*>(a.refs), T(a.ref_scalar), T(a.flo), T(a.fhi));
+        return cudaGetLastError();
+    }
     filter_warp_kernel<T, W, false, kNB><<<grid, kThreads, 0, a.stream>>>(
         static_cast<const char*>(a.in), static_cast<unsigned char*>(a.out), a.counts, a.n_blocks,
         static_cast<const T*>(a.refs), T(a.ref_scalar), T(a.flo), T(a.fhi));
@@ -405,8 +416,13 @@ static cudaError_t do_select(const LaunchArgs& a) {
 }
 template <class T, int W>
 static cudaError_t do_delta_filter(const LaunchArgs& a) {
-    const unsigned grid = unsigned((a.n_blocks * 32 + kThreads - 1) / kThreads);
-    delta_filter_warp_kernel<T, W, false><<<grid, kThreads, 0, a.stream>>>(
+    // Blocks per warp, with the loads of block b + 1 issued before block b is evaluated (fl_scan.cuh).  8 where it measured
+    // faster (u8: 1.89 -> 1.58 ms at W = 1, 2.09 -> 1.66 at W = 8; u16 W <= 4: 876 -> 756 us; u32 W <= 17: 471 -> 380 us at
+    // W = 1), 1 where the second register set costs more than the hidden latency (u16 W >= 9, u32 W >= 29, u64 W = 16);
+    // profiles/opbench_filter_pipe_r02.txt.
+    constexpr int kNB = sizeof(T) == 1 ? 8 : (sizeof(T) == 2 ? (W <= 4 ? 8 : 1) : (sizeof(T) == 4 ? (W <= 17 ? 8 : 1) : 1));
+    const unsigned grid = unsigned((((a.n_blocks + kNB - 1) / kNB) * 32 + kThreads - 1) / kThreads);
+    delta_filter_warp_kernel<T, W, kNB><<<grid, kThreads, 0, a.stream>>>(
         static_cast<const char*>(a.in), static_cast<const char*>(a.base), static_cast<unsigned char*>(a.out), a.counts,
         a.n_blocks, T(a.flo), T(a.fhi));
     return cudaGetLastError();

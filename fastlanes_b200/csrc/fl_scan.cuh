@@ -21,6 +21,40 @@
 
 namespace flb {
 
+// ---- one-block-ahead loads ---------------------------------------------------------------------------------------
+// The scan kernels run NB consecutive blocks per warp.  Their per-block work is a few hundred instructions behind one DRAM
+// round trip, so a warp that loads, waits and computes block after block idles for most of its life (ncu, select with one
+// block per warp: 29 % of all warp samples on the first use of the loaded words, profiles/ncu_r02_select.md).  RunLoads
+// holds a thread's slices of the packed word-rows of its run as raw registers: issue() for block b + 1 is called before
+// block b is processed, assemble() applies the alignment shifts of warp_run_from at the point of use.
+template <class T, int W>
+__host__ __device__ constexpr int run_loads() {  // word-row loads warp_run_from issues for one thread
+    constexpr int TB = Lay<T>::TB, RPG = TB / 4;
+    return W == 0 ? 0 : (W == TB ? RPG : ((W % 4) == 0 ? run_words<T, W>() : run_words<T, W>() + 1));
+}
+template <class T, int W>
+struct RunLoads {
+    uint4 raw[run_loads<T, W>() > 0 ? run_loads<T, W>() : 1];
+    __device__ __forceinline__ void issue(const char* __restrict__ blk_packed, int q, int j) {
+        if constexpr (W > 0) {
+            const char* pk = blk_packed + j * 16;
+            int n = 0;
+            Slice<T> unused[run_words<T, W>()];  // the shifts are dead here
+            warp_run_from<T, W>([&](unsigned k) -> Slice<T> { raw[n] = ldg128_stream(pk + k * 128); return to_slice<T>(raw[n++]); }, q, unused);
+        }
+    }
+    __device__ __forceinline__ void assemble(int q, Slice<T> (&a)[run_words<T, W>()]) const {
+        int n = 0;
+        warp_run_from<T, W>([&](unsigned) -> Slice<T> { return to_slice<T>(raw[n++]); }, q, a);
+    }
+    __device__ __forceinline__ uint32_t any_word() const {  // a value that depends on every load
+        uint32_t d = 0;
+#pragma unroll
+        for (int n = 0; n < run_loads<T, W>(); ++n) d |= raw[n].x;
+        return d;
+    }
+};
+
 // Predicate bits of one 16-byte slice, ORed into `acc` at bit position POS: bit POS+k = lane k passes
 // (v - c) <= span  (lane-wise, wrapping, unsigned).  spanH = span | H for the SWAR types.
 template <class T, int POS>
@@ -119,7 +153,7 @@ struct FilterPred {
 
 // NB consecutive blocks per warp: the per-warp set-up (thread mapping, tile address, and — with a scalar reference —
 // the whole FilterPred) is paid once per NB blocks; the filter is issue-bound below W ~ 3T/4, so this is throughput.
-template <class T, int W, bool TMA, int NB>
+template <class T, int W, bool TMA, int NB, bool PIPE = false>
 __global__ void __launch_bounds__(kThreads)
 filter_warp_kernel(const char* __restrict__ packed, unsigned char* __restrict__ bitmap, uint32_t* __restrict__ counts,
                    size_t n_blocks, const T* __restrict__ refs, T ref_scalar, T lo, T hi) {
@@ -137,13 +171,18 @@ filter_warp_kernel(const char* __restrict__ packed, unsigned char* __restrict__ 
     unsigned char* tile = scan_tile[threadIdx.x >> 5];
     FilterPred<T, W> pred(ref_scalar, lo, hi);
 
-#pragma unroll 1
-    for (int nb = 0; nb < NB; ++nb) {
-        const size_t blk = blk0 + nb;
-        if (blk >= n_blocks) break;  // warp-uniform
-        if (refs != nullptr) pred = FilterPred<T, W>(refs[blk], lo, hi);
+    // one block; with PIPE the packed words of block blk + 1 are requested before block blk is evaluated (RunLoads)
+    auto one_block = [&](size_t blk, bool more, const RunLoads<T, W>& cur, RunLoads<T, W>& nxt, T ref_cur, T& ref_nxt) {
+        if constexpr (PIPE) {
+            if (more) {
+                nxt.issue(packed + (blk + 1) * (size_t(128) * W), q, j);
+                if (refs != nullptr) ref_nxt = refs[blk + 1];
+            }
+        }
+        if (refs != nullptr) pred = FilterPred<T, W>(PIPE ? ref_cur : refs[blk], lo, hi);
         Slice<T> a[run_words<T, W>()];
-        warp_load_run<T, W, TMA, (kThreads / 32) * 128>(packed + blk * (size_t(128) * W), lane, q, j, a);
+        if constexpr (PIPE) cur.assemble(q, a);
+        else warp_load_run<T, W, TMA, (kThreads / 32) * 128>(packed + blk * (size_t(128) * W), lane, q, j, a);
 
         // value = v + ref (ffor.rs:47, wrapping).  lo <= value <= hi  <=>  (v - c) mod 2^T <= span, c = lo - ref, span = hi - lo
         uint32_t x = 0;
@@ -213,6 +252,24 @@ filter_warp_kernel(const char* __restrict__ packed, unsigned char* __restrict__ 
             if (lane == 0) counts[blk] = n;
         }
         __syncwarp();  // the tile is rewritten by the next block
+    };
+
+    const size_t blk_end = (n_blocks - blk0 < size_t(NB)) ? n_blocks : blk0 + NB;
+    RunLoads<T, W> ld0, ld1;
+    T r0 = ref_scalar, r1 = ref_scalar;
+    if constexpr (PIPE) {
+        static_assert(!TMA && (NB == 1 || NB % 2 == 0), "pipelined loads: direct loads, block loop unrolled by two");
+        ld0.issue(packed + blk0 * (size_t(128) * W), q, j);
+        if (refs != nullptr) r0 = refs[blk0];
+#pragma unroll 1
+        for (size_t blk = blk0; blk < blk_end; blk += 2) {
+            one_block(blk, blk + 1 < blk_end, ld0, ld1, r0, r1);
+            if (blk + 1 >= blk_end) break;
+            one_block(blk + 1, blk + 2 < blk_end, ld1, ld0, r1, r0);
+        }
+    } else {
+#pragma unroll 1
+        for (size_t blk = blk0; blk < blk_end; ++blk) one_block(blk, false, ld0, ld1, r0, r1);
     }
 }
 
@@ -350,7 +407,8 @@ filter_u16_slice_kernel(const char* __restrict__ packed, unsigned char* __restri
 // Decode and prefix-add exactly as unpack_warp_kernel<UOP_DELTA>; the predicate bits are kept lane-major so that
 // every thread owns whole bytes of the original-order bitmap (fl_scan_bits.h, "delta scan").
 // ---------------------------------------------------------------------------------------------------
-template <class T, int W, bool TMA>
+// NB consecutive blocks per warp; the loads of block b + 1 (packed words and bases) are issued before block b is evaluated.
+template <class T, int W, int NB>
 __global__ void __launch_bounds__(kThreads)
 delta_filter_warp_kernel(const char* __restrict__ packed, const char* __restrict__ base, unsigned char* __restrict__ bitmap,
                          uint32_t* __restrict__ counts, size_t n_blocks, T lo, T hi) {
@@ -359,14 +417,25 @@ delta_filter_warp_kernel(const char* __restrict__ packed, const char* __restrict
     constexpr int TB = Lay<T>::TB;
     constexpr int RPG = WL::RPG;
     constexpr int NR = Lay<T>::NR;
-    const size_t blk = (size_t(blockIdx.x) * kThreads + threadIdx.x) >> 5;
-    if (blk >= n_blocks) return;  // warp-uniform
+    static_assert(NB == 1 || NB % 2 == 0, "block loop unrolled by two");
+    const size_t blk0 = ((size_t(blockIdx.x) * kThreads + threadIdx.x) >> 5) * NB;
+    if (blk0 >= n_blocks) return;  // warp-uniform
     const int lane = threadIdx.x & 31;
     const int g = lane >> 3, j = lane & 7;
     const int q = WL::rank_of_group(g);
-    Slice<T> carry = load_slice<T>(base + blk * 128 + j * 16);  // prev = base[lane] (delta.rs:50), before the TMA wait
+    __shared__ __align__(16) unsigned char scan_tile[kThreads / 32][128];
+    unsigned char* tile = scan_tile[threadIdx.x >> 5];
+
+    auto one_block = [&](size_t blk, bool more, const RunLoads<T, W>& cur, RunLoads<T, W>& nxt, const uint4& base_cur, uint4& base_nxt) {
+    if (more) {
+        nxt.issue(packed + (blk + 1) * (size_t(128) * W), q, j);
+        base_nxt = ldg128_stream(base + (blk + 1) * 128 + j * 16);
+    }
+    Slice<T> carry = to_slice<T>(base_cur);  // prev = base[lane] (delta.rs:50)
+    Slice<T> a[run_words<T, W>()];
+    cur.assemble(q, a);
     Slice<T> v[RPG];
-    warp_decode_tile<T, W, TMA, (kThreads / 32) * 128>(packed + blk * (size_t(128) * W), lane, q, j, v);
+    warp_extract_rows<T, W>(a, v);
 
     // delta.rs:56-60: running wrapping sum along rows per lane (same as unpack_warp_kernel<UOP_DELTA>)
 #pragma unroll
@@ -408,8 +477,6 @@ delta_filter_warp_kernel(const char* __restrict__ packed, const char* __restrict
     }
     if (hi < lo) x = 0;  // empty range
 
-    __shared__ __align__(16) unsigned char scan_tile[kThreads / 32][128];
-    unsigned char* tile = scan_tile[threadIdx.x >> 5];
     // u8 / u16: rank == group, so the thread holding the same lanes at rank q^1 (q^2) is lane^8 (lane^16)
     if constexpr (sizeof(T) == 2) {
         x = merge_pair_bpt4(x, __shfl_xor_sync(0xffffffffu, x, 8), q);
@@ -424,6 +491,24 @@ delta_filter_warp_kernel(const char* __restrict__ packed, const char* __restrict
     if (counts != nullptr) {
         const uint32_t n = __reduce_add_sync(0xffffffffu, uint32_t(__popc(word)));
         if (lane == 0) counts[blk] = n;
+    }
+    if (NB > 1) __syncwarp();  // the tile is rewritten by the next block
+    };
+
+    const size_t blk_end = (n_blocks - blk0 < size_t(NB)) ? n_blocks : blk0 + NB;
+    RunLoads<T, W> ld0, ld1;
+    uint4 b0, b1;
+    ld0.issue(packed + blk0 * (size_t(128) * W), q, j);
+    b0 = ldg128_stream(base + blk0 * 128 + j * 16);
+    if constexpr (NB == 1) {
+        one_block(blk0, false, ld0, ld1, b0, b1);
+    } else {
+#pragma unroll 1
+        for (size_t blk = blk0; blk < blk_end; blk += 2) {
+            one_block(blk, blk + 1 < blk_end, ld0, ld1, b0, b1);
+            if (blk + 1 >= blk_end) break;
+            one_block(blk + 1, blk + 2 < blk_end, ld1, ld0, b1, b0);
+        }
     }
 }
 
@@ -472,19 +557,13 @@ __device__ __forceinline__ typename Lay<T>::R slice_lane_low(const Slice<T>& s, 
     return s.r[k / LPR] >> (Lay<T>::TB * (k % LPR));
 }
 
-// number of word-row loads warp_run_from issues for one thread
-template <class T, int W>
-__host__ __device__ constexpr int run_loads() {
-    constexpr int TB = Lay<T>::TB, RPG = TB / 4;
-    return W == 0 ? 0 : (W == TB ? RPG : ((W % 4) == 0 ? run_words<T, W>() : run_words<T, W>() + 1));
-}
 // everything a block's compaction needs from global memory, loaded one block ahead of its use
 template <class T, int W>
 struct SelectLoads {
     uint32_t mword;  // this lane's word of the block bitmap
     uint64_t obase;  // offsets[blk]
     T ref;
-    uint4 raw[run_loads<T, W>() > 0 ? run_loads<T, W>() : 1];  // this thread's slices of the word-rows of its run
+    RunLoads<T, W> run;  // this thread's slices of the word-rows of its run
 };
 template <class T, int W>
 __device__ __forceinline__ void select_issue_loads(SelectLoads<T, W>& ld, size_t blk, int lane, int q, int j,
@@ -493,12 +572,7 @@ __device__ __forceinline__ void select_issue_loads(SelectLoads<T, W>& ld, size_t
     ld.mword = reinterpret_cast<const uint32_t*>(bitmap + blk * 128)[lane];
     ld.obase = offsets[blk];
     ld.ref = refs ? refs[blk] : ref_scalar;
-    if constexpr (W > 0) {
-        const char* pk = packed + blk * (size_t(128) * W) + j * 16;
-        int n = 0;
-        Slice<T> unused[run_words<T, W>()];  // the alignment shifts happen at the point of use (dead here)
-        warp_run_from<T, W>([&](unsigned k) -> Slice<T> { ld.raw[n] = ldg128_stream(pk + k * 128); return to_slice<T>(ld.raw[n++]); }, q, unused);
-    }
+    ld.run.issue(packed + blk * (size_t(128) * W), q, j);
 }
 
 template <class T, int W, int NB>
@@ -559,10 +633,7 @@ select_warp_kernel(const char* __restrict__ packed, const unsigned char* __restr
         // exit on whose path they are dead — with one block per warp that puts the bitmap and the packed round trips in
         // series.  Taking the long path with total == 0 is harmless (every store is predicated on a set bit, the drain is
         // empty), so the extra condition may be anything the compiler cannot fold.
-        uint32_t dep = 0;
-#pragma unroll
-        for (int n = 0; n < run_loads<T, W>(); ++n) dep |= cur.raw[n].x;
-        if (total == 0 && __all_sync(0xffffffffu, dep != 0x5bd1e995u)) return;  // the vote keeps the branch warp-uniform
+        if (total == 0 && __all_sync(0xffffffffu, cur.run.any_word() != 0x5bd1e995u)) return;  // the vote keeps the branch uniform  // the vote keeps the branch warp-uniform
         T* o = out + cur.obase;
         const uint32_t mis = uint32_t((reinterpret_cast<uintptr_t>(o) & 15u) / sizeof(T));  // phase of the run inside a 16-byte vector
         // (the previous block's table look-ups ended before its pre-drain __syncwarp, and its drain reads end before any lane
@@ -571,10 +642,7 @@ select_warp_kernel(const char* __restrict__ packed, const unsigned char* __restr
         __syncwarp();
 
         Slice<T> a[run_words<T, W>()];
-        {
-            int n = 0;
-            warp_run_from<T, W>([&](unsigned) -> Slice<T> { return to_slice<T>(cur.raw[n++]); }, q, a);
-        }
+        cur.run.assemble(q, a);
         Slice<T> v[RPG];
         warp_extract_rows<T, W>(a, v);
 #pragma unroll
