@@ -77,3 +77,7 @@ build/test_scan_bits: tests/cpp/test_scan_bits.cpp $(SRC)/fl_scan_bits.h
 # latency of the single-block drop-in call from compiled host code (tools/latbench.cpp)
 build/latbench: tools/latbench.cpp include/fastlanes_b200.h $(LIB)
 	g++ -std=c++17 -O2 -Iinclude -o $@ $< -Lfastlanes_b200/lib -lfastlanes_b200 -Wl,-rpath,'$$ORIGIN/../fastlanes_b200/lib'
+
+# mid-size host calls (the reference's 1024-block throughput bench shape) from compiled host code (tools/midbench.cpp)
+build/midbench: tools/midbench.cpp include/fastlanes_b200.h $(LIB)
+	g++ -std=c++17 -O2 -Iinclude -o $@ $< -Lfastlanes_b200/lib -lfastlanes_b200 -Wl,-rpath,'$$ORIGIN/../fastlanes_b200/lib'

@@ -318,7 +318,7 @@ bool alloc_placed(void** out, size_t bytes, const std::vector<NodeRange>& ranges
         if (sys_mbind(static_cast<char*>(p) + b, e - b, kMpolPreferred, &mask, 64, 0) == 0) bound = true;
     }
     if (!bound) { munmap(p, len); return false; }  // mbind refused (seccomp / no permission): nothing gained
-    if (cudaHostRegister(p, len, cudaHostRegisterDefault) != cudaSuccess) {
+    if (cudaHostRegister(p, len, cudaHostRegisterPortable | cudaHostRegisterMapped) != cudaSuccess) {
         (void)cudaGetLastError();
         munmap(p, len);
         return false;
@@ -342,6 +342,9 @@ struct Slot {
     void* d_base = nullptr;
     size_t in_cap = 0, out_cap = 0, base_cap = 0;
 };
+#ifndef FLB_DIRECT_MAX_DEFAULT
+#define FLB_DIRECT_MAX_DEFAULT (size_t(512) << 20)
+#endif
 constexpr size_t kSmallBytes = size_t(256) << 10;  // low-latency path: in + base + out of the whole call fit in this
 struct Lane {
     std::mutex mu;
@@ -472,6 +475,24 @@ inline bool small_path_enabled() {
     return on;
 }
 
+// FLB_DIRECT_MAX=<bytes>: largest call (input + bases + output) that takes the direct path below; 0 disables it.
+inline size_t direct_max_bytes() {
+    static const size_t v = [] {
+        const char* e = std::getenv("FLB_DIRECT_MAX");
+        return e ? size_t(std::strtoull(e, nullptr, 10)) : size_t(FLB_DIRECT_MAX_DEFAULT);
+    }();
+    return v;
+}
+// Device-visible address of a PAGE-LOCKED host pointer (cudaHostAlloc / cudaHostRegister / fl_host_alloc), or false for
+// pageable memory.  ~0.3 us per call.
+inline bool pinned_device_ptr(const void* host, const void** dev) {
+    cudaPointerAttributes at;
+    if (cudaPointerGetAttributes(&at, host) != cudaSuccess) { (void)cudaGetLastError(); return false; }
+    if (at.type != cudaMemoryTypeHost || at.devicePointer == nullptr) return false;
+    *dev = at.devicePointer;
+    return true;
+}
+
 template <class T>
 fl_status host_op(Op op, unsigned width, size_t n_blocks, const void* in, void* out, const void* base,
                   uint64_t ref_scalar) {
@@ -510,6 +531,29 @@ fl_status host_op(Op op, unsigned width, size_t n_blocks, const void* in, void* 
         if (e != cudaSuccess && result == FL_OK) result = cuda_fail(e, "cudaStreamSynchronize");
         if (result == FL_OK) std::memcpy(out, h_out, out_sz);
         return result;
+    }
+
+    // ---- direct path: mid-size calls on page-locked caller buffers ----------------------------------------------------
+    // The reference's own throughput bench shape (benches/bitpacking.rs:67-98: 1024 blocks = 2 MiB) is one pipeline chunk:
+    // H2D copy, kernel, D2H copy run back to back on one stream, three operations and two trips through HBM for a transfer
+    // the link finishes in ~40 us.  When every buffer of the call is page-locked the kernel addresses the caller's memory
+    // itself (UVA zero-copy, as the low-latency path does through its bounce buffer): ONE launch streams the packed words in
+    // and the decoded values out over PCIe concurrently, one synchronise.  Measured (tools/midbench.cpp,
+    // profiles/midbench_r02.txt): 1024 blocks u16 W=3 69.7 -> 55.2 us, 64 blocks u32 W=10 32.7 -> 18.7 us, 65536 blocks u32
+    // (335 MB moved) 6.3-6.8 -> 5.6 ms.  SM-issued PCIe writes top out near 48 GB/s where the copy engines reach 52-55, so
+    // above FLB_DIRECT_MAX (default 512 MiB per call) the chunked copy-engine pipeline, which needs many chunks in flight
+    // to reach that ceiling, takes over.
+    if (n_blocks * (ib + bb + ob) <= direct_max_bytes() && n_blocks <= kMaxBlocksPerLaunch) {
+        const void *d_in = nullptr, *d_out = nullptr, *d_base = nullptr;
+        const bool aligned = ((reinterpret_cast<uintptr_t>(in) | reinterpret_cast<uintptr_t>(out) | reinterpret_cast<uintptr_t>(base)) & 15u) == 0;
+        if (aligned && (!ib || pinned_device_ptr(in, &d_in)) && pinned_device_ptr(out, &d_out) && (!bb || pinned_device_ptr(base, &d_base))) {
+            if (lane.slots.empty()) lane.slots.resize(1);
+            if (fl_status st = ensure_stream(lane.slots[0])) return st;
+            fl_status result = device_op<T>(op, width, n_blocks, d_in, const_cast<void*>(d_out), d_base, nullptr, ref_scalar, lane.slots[0].stream);
+            const cudaError_t e = cudaStreamSynchronize(lane.slots[0].stream);
+            if (e != cudaSuccess && result == FL_OK) result = cuda_fail(e, "cudaStreamSynchronize");
+            return result;
+        }
     }
 
     return run_pipeline(
@@ -585,6 +629,26 @@ fl_status host_filter(unsigned width, size_t n_blocks, const T* packed, const T*
     LaneLock lk;
     if (fl_status s = acquire_lane(&lk)) return s;
     const size_t ib = size_t(128) * width;
+    // direct path (see host_op): every buffer page-locked and the call below FLB_DIRECT_MAX -> one launch on the caller's memory
+    if (n_blocks * (ib + 132 + (base ? 128 : 0)) <= direct_max_bytes() && n_blocks <= kMaxBlocksPerLaunch) {
+        const void *d_in = nullptr, *d_base = nullptr, *d_bm = nullptr, *d_cnt = nullptr;
+        const bool aligned = ((reinterpret_cast<uintptr_t>(packed) | reinterpret_cast<uintptr_t>(base) | reinterpret_cast<uintptr_t>(bitmap)) & 15u) == 0 &&
+                             (reinterpret_cast<uintptr_t>(counts) & 3u) == 0;
+        if (aligned && (!ib || pinned_device_ptr(packed, &d_in)) && (!base || pinned_device_ptr(base, &d_base)) &&
+            pinned_device_ptr(bitmap, &d_bm) && (!counts || pinned_device_ptr(counts, &d_cnt))) {
+            Lane& lane = *lk.lane;
+            if (lane.slots.empty()) lane.slots.resize(1);
+            if (fl_status st = ensure_stream(lane.slots[0])) return st;
+            cudaStream_t stream = lane.slots[0].stream;
+            uint8_t* bm = static_cast<uint8_t*>(const_cast<void*>(d_bm));
+            uint32_t* cn = static_cast<uint32_t*>(const_cast<void*>(d_cnt));
+            fl_status result = base ? device_delta_filter<T>(width, n_blocks, static_cast<const T*>(d_in), static_cast<const T*>(d_base), lo, hi, bm, cn, stream)
+                                    : device_filter<T>(width, n_blocks, static_cast<const T*>(d_in), nullptr, reference, lo, hi, bm, cn, stream);
+            const cudaError_t e = cudaStreamSynchronize(stream);
+            if (e != cudaSuccess && result == FL_OK) result = cuda_fail(e, "cudaStreamSynchronize");
+            return result;
+        }
+    }
     const size_t cb_max = std::min(n_blocks, pipe_cfg().chunk);
     return run_pipeline(
         *lk.lane, n_blocks,
@@ -892,7 +956,7 @@ fl_status fl_host_alloc(void** p, size_t bytes) {
         if (node >= 0 && alloc_placed(p, bytes, {NodeRange{0, bytes, node}})) return FL_OK;
     }
     (void)cudaGetLastError();
-    const cudaError_t err = cudaHostAlloc(p, bytes, cudaHostAllocDefault);
+    const cudaError_t err = cudaHostAlloc(p, bytes, cudaHostAllocPortable | cudaHostAllocMapped);
     if (err != cudaSuccess) return cuda_fail(err, "cudaHostAlloc");
     return FL_OK;
 }
@@ -922,7 +986,7 @@ int fl_host_buffer_node(const void* p) {
 }
 fl_status fl_host_register(void* p, size_t bytes) {
     if (!p) return fail(FL_ERR_NULL, "null pointer");
-    FL_CUDA(cudaHostRegister(p, bytes, cudaHostRegisterDefault));
+    FL_CUDA(cudaHostRegister(p, bytes, cudaHostRegisterPortable | cudaHostRegisterMapped));
     return FL_OK;
 }
 fl_status fl_host_unregister(void* p) {

@@ -149,6 +149,40 @@ def test_pinned_buffers(fl, oracle):
     assert np.array_equal(out, oracle.unpack(np.array(packed), w, threads=4))
 
 
+@pytest.mark.parametrize("tb", [8, 16, 32, 64])
+def test_direct_path_page_locked_buffers(fl, oracle, tb):
+    """Mid-size calls whose buffers are ALL page-locked run as one launch on the caller's memory (no staging copies):
+    every op family, widths incl. 0 and T, block counts above the 256 KiB low-latency limit, against the oracle; then the
+    same call with one pageable buffer (the chunked pipeline) must give the same bytes."""
+    rng = np.random.default_rng(1200 + tb)
+    n = 2 * ((256 << 10) // (128 * tb)) + 37
+    for w in (0, 1, tb // 2 + 1, tb - 1, tb):
+        values = fl.pinned_empty(n * 1024, DT[tb]); values[:] = rand_bytes(rng, n * 128 * tb, tb)
+        base = fl.pinned_empty(n * (1024 // tb), DT[tb]); base[:] = rand_bytes(rng, n * 128, tb)
+        packed = fl.pinned_empty(max(1, n * 1024 * w // tb), DT[tb])[: n * 1024 * w // tb]
+        out = fl.pinned_empty(n * 1024, DT[tb])
+        fl.BitPacking.pack(w, values, packed)
+        assert np.array_equal(packed, oracle.pack(np.array(values), w, threads=4)), (tb, w)
+        out[:] = 0x5A
+        fl.BitPacking.unpack(w, packed, out)
+        assert np.array_equal(out, oracle.unpack(np.array(packed), w, n_blocks=n, threads=4)), (tb, w)
+        ref = int(rng.integers(0, 1 << min(tb, 62)))
+        fl.FoR.unfor_pack(w, packed, ref, out)
+        assert np.array_equal(out, oracle.unfor_pack(np.array(packed), ref, w, n_blocks=n)), (tb, w)
+        fl.Delta.undelta_pack(w, packed, base, out)
+        want = oracle.undelta_pack(np.array(packed), np.array(base), w, n_blocks=n)
+        assert np.array_equal(out, want), (tb, w)
+        pageable_out = np.zeros(n * 1024, dtype=DT[tb])
+        fl.Delta.undelta_pack(w, packed, base, pageable_out)
+        assert np.array_equal(pageable_out, want), (tb, w)
+        fl.Delta.transpose_delta_pack(w, values, base, packed)
+        fl.Delta.undelta_pack_untranspose(w, packed, base, out)
+        if w == tb:
+            assert np.array_equal(out, values), (tb, w)
+    fl.Transpose.transpose(values, out)
+    assert np.array_equal(out, oracle.transpose(np.array(values))), tb
+
+
 def test_small_calls_every_op_and_size_boundary(fl, oracle):
     """The low-latency path (zero-copy page-locked staging, one launch) takes calls whose in + base + out fit in 256 KiB;
     the block counts here straddle that limit for every type so both paths are compared with the oracle."""

@@ -166,6 +166,13 @@ def test_filter_host_path(fl, oracle, tb):
             fl.Scan.filter_range(w, packed, ref, lo, hi, bitmap, counts)
             assert np.array_equal(bitmap, want), (tb, w)
             assert np.array_equal(counts, sel.reshape(n, 1024).sum(1).astype(np.uint32))
+            # the same call with every buffer page-locked: one launch on the caller's memory (direct path), same bytes
+            p_packed = fl.pinned_empty(max(1, packed.size), DT[tb])[: packed.size]; p_packed[:] = packed
+            p_bitmap = fl.pinned_empty(n * 128, np.uint8); p_bitmap[:] = 0
+            p_counts = fl.pinned_empty(n, np.uint32); p_counts[:] = 0
+            fl.Scan.filter_range(w, p_packed, ref, lo, hi, p_bitmap, p_counts)
+            assert np.array_equal(p_bitmap, want), (tb, w, "direct")
+            assert np.array_equal(p_counts, counts), (tb, w, "direct")
     finally:
         fl.host_configure(0, 0)
 
