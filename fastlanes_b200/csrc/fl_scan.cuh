@@ -449,19 +449,21 @@ delta_filter_warp_kernel(const char* __restrict__ packed, const char* __restrict
             if (qq < q) carry.r[r] = lane_add<T>(carry.r[r], t);
         }
     }
+    // lo <= value <= hi  <=>  (value - lo) mod 2^T <= hi - lo.  The subtraction of lo rides on the carry (one lane-wise
+    // subtract per register of the carry instead of one per value): v[i] becomes value - lo.  Bits LANE-major: bit k*RPG + i
+    const Slice<T> cs = slice_splat<T>(lo), ss = slice_splat<T>(T(hi - lo));
+    carry = slice_sub<T>(carry, cs);
 #pragma unroll
     for (int i = 0; i < RPG; ++i) v[i] = slice_add<T>(v[i], carry);
 
-    // lo <= value <= hi  <=>  (value - lo) mod 2^T <= hi - lo; bits LANE-major: bit k*RPG + i
     uint32_t x = 0;
-    const Slice<T> cs = slice_splat<T>(lo), ss = slice_splat<T>(T(hi - lo));
-    const R c = cs.r[0], span = ss.r[0];
+    const R span = ss.r[0];
     if constexpr (sizeof(T) >= 4) {
         const R not_span = ~span;
 #pragma unroll
         for (int r = NR - 1; r >= 0; --r)  // descending bit position: the last value shifted in lands at bit 0
 #pragma unroll
-            for (int i = RPG - 1; i >= 0; --i) shift_in_fail(x, R(v[i].r[r] - c), not_span);
+            for (int i = RPG - 1; i >= 0; --i) shift_in_fail(x, v[i].r[r], not_span);
         x = ~x;
     } else {
         const R spanH = span | rep_value<T>(T(T(1) << (TB - 1)));
@@ -469,7 +471,7 @@ delta_filter_warp_kernel(const char* __restrict__ packed, const char* __restrict
             constexpr int i = decltype(ic)::value;
 #pragma unroll
             for (int r = 0; r < 4; ++r) {
-                const uint32_t le = swar_leu_top<TB>(lane_sub<T>(v[i].r[r], c), span, spanH);
+                const uint32_t le = swar_leu_top<TB>(v[i].r[r], span, spanH);
                 if constexpr (sizeof(T) == 2) x |= top_bits_lane_major_u16(le) << (8 * r + i);
                 else x |= top_bits_lane_major_u8(le) << (8 * r + i);
             }
