@@ -545,6 +545,8 @@ delta_filter_warp_kernel(const char* __restrict__ packed, const char* __restrict
 template <class T>
 __host__ __device__ constexpr int select_stage_bytes() { return 1024 * int(sizeof(T)) + 16; }
 
+// Stores the low sizeof(T) bytes of `x` at shared address `sa` (st.shared.u8 / .u16 truncate the wider source register, so the
+// SWAR types pass their register shifted down to the lane without masking it: one instruction less per value).
 template <class T>
 __device__ __forceinline__ void sts_low(uint32_t sa, typename Lay<T>::R x) {
     if constexpr (sizeof(T) == 1) asm volatile("st.shared.u8 [%0], %1;" ::"r"(sa), "r"(x) : "memory");

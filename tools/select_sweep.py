@@ -1,7 +1,8 @@
 #!/usr/bin/env python
-"""tools/select_sweep.py [TBITS ...] — fl_unpack_select at 25 % selectivity, every width of the given types, in the variant
-the environment selects (FLB_SELECT / FLB_SELECT_NB); prints `T W us GB/s`.  Run once per variant on the same box and
-compare (tools/gpu_r02_l.sh).  Measurement tool only."""
+"""tools/select_sweep.py [TBITS ...] — fl_unpack_select at 25 % selectivity, every width of the given types; prints
+`T W us GB/s`.  profiles/select_sweep_r02.txt was produced with a development build in which FLB_SELECT / FLB_SELECT_NB chose
+the kernel variant and the blocks per warp (tools/gpu_r02_l.sh); the shipped library instantiates only the chosen form per
+type / width (select_nb() in fl_codec_inst.cu).  Measurement tool only."""
 import os
 import statistics
 import sys
