@@ -586,6 +586,35 @@ def end_to_end(D: Dev, fl, np, packed, out, n_blocks, e2e_steps, launch):
             "value": round(ints_per_step / f_s / 1e9, 2), "unit": "Gint/s scanned", "h2d_bytes_per_step": h2d,
             "d2h_bytes_per_step": len(WIDTHS) * n_blocks * 132, "ms_per_step": round(f_s * 1e3, 1), "steps": 1,
             "api": "fl_host_unpack_filter_u32: range predicate lo<=v<=hi per width, bitmap + counts to page-locked host memory"}
+    # ---- the reference's own throughput bench shape (benches/bitpacking.rs:67-98: u16, W = 3, 1024 blocks = 2 MiB) through
+    # the host family on page-locked buffers: one launch on the caller's memory (the direct path of host_op).  Rank 0 only.
+    if D.rank == 0:
+        try:
+            nb = 1024
+            v16 = fl.pinned_empty(nb * 1024, np.uint16); v16[:] = (np.arange(nb * 1024) % 8).astype(np.uint16)
+            p16 = fl.pinned_empty(nb * 192, np.uint16)
+            u16 = fl.pinned_empty(nb * 1024, np.uint16)
+            pack16, unpack16 = _lib.fn("fl_host_pack", 16), _lib.fn("fl_host_unpack", 16)
+
+            def med_us(fn, k=60):
+                for _ in range(5):
+                    fn()
+                ts = []
+                for _ in range(k):
+                    t0 = time.perf_counter(); fn(); ts.append(time.perf_counter() - t0)
+                return statistics.median(ts) * 1e6
+
+            tp = med_us(lambda: pack16(3, nb, v16.ctypes.data, p16.ctypes.data))
+            tu = med_us(lambda: unpack16(3, nb, p16.ctypes.data, u16.ctypes.data))
+            assert np.array_equal(u16, v16), "1024-block round trip through the host family"
+            e2e["ref_bench_shape"] = {
+                "workload": "benches/bitpacking.rs:67-98: u16 W=3, 1024 blocks (2 MiB unpacked), page-locked host buffers",
+                "compress_us": round(tp, 1), "decompress_us": round(tu, 1),
+                "decompress_GBps_unpacked": round(nb * 2048 / tu / 1e3, 2),
+                "api": "fl_host_pack_u16 / fl_host_unpack_u16: one launch on the caller's page-locked memory (direct path), host wall clock, median of 60 calls"}
+            del v16, p16, u16
+        except (fl.FastLanesError, MemoryError) as exc:  # reported, never fatal for the headline
+            e2e["ref_bench_shape"] = {"error": str(exc)}
     del h_packed, h_out, h_bitmap, h_counts
     return e2e
 
@@ -734,6 +763,14 @@ def main():
         dt, ints = cpu_sweep(oracle, np, lg, threads, 3)
         dt1, ints1 = cpu_sweep(oracle, np, 13, 1, 2)
         fdt, fints = cpu_filter_sweep(oracle, np, lg, threads, 2)
+        # the reference's throughput bench shape on one thread, as criterion runs it (benches/bitpacking.rs:67-98)
+        rb_v = (np.arange(1024 * 1024) % 8).astype(np.uint16)
+        rb_p = oracle.pack(rb_v, 3)
+        rb_u = np.zeros_like(rb_v)
+        rb_t = []
+        for _ in range(25):
+            t0 = time.perf_counter(); oracle.run_raw(16, oracle.OP_UNPACK, 3, 1024, rb_p, rb_u); rb_t.append(time.perf_counter() - t0)
+        rb_us = statistics.median(rb_t[5:]) * 1e6
         if samples is not None:  # the oracle as checker of the sharded decode (sampled blocks at the shard boundaries)
             ok = all(np.array_equal(oracle.unpack(p.view(np.uint32), samples["width"], n_blocks=1), d.view(np.uint32))
                      for p, d in zip(samples["packed"], samples["decoded"]))
@@ -743,6 +780,7 @@ def main():
                "sample": f"u32 unpack W=1..32, 2^{lg} blocks per width (the whole config; best of 3 passes), host memory, {oracle.isa()}, {threads} threads (fastest probed; {hw} logical CPUs visible, cgroup CPU quota {quota})",
                "single_thread_Gints": round(ints1 / dt1 / 1e9, 3),
                "scan_filter_Gints": round(fints / fdt / 1e9, 3),
+               "ref_bench_shape_decompress_us_1thread": round(rb_us, 1),
                "scan_filter_note": "same threads: unfor_pack into a 4 KiB per-thread scratch + range-predicate loop -> bitmap (what a user of the reference writes, README.md:40-41); compare with e2e.scan_filter",
                "note": "C++ restatement of the reference loops (the Rust crate cannot be built here); a reported baseline, not the target"}
 
