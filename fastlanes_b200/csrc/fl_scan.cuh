@@ -609,12 +609,11 @@ select_warp_kernel(const char* __restrict__ packed, const unsigned char* __restr
     uint32_t sh[BANDS], lowmask[BANDS];
 #pragma unroll
     for (int bnd = 0; bnd < BANDS; ++bnd) {
-        const int r0 = q * RPG + bnd * 8;  // first global row of the band (RPG < 8: of the run)
-        const int c0 = scan_fl_order(r0 >> 3) * 16 + (r0 & 7) * 128 + j * BPT;
+        const int c0 = select_band_origin<TB>(q, bnd, j);  // fl_scan_bits.h (checked on the CPU by tests/cpp/test_scan_bits.cpp)
         trow[bnd] = tile + (c0 >> 5);
         const uint32_t s0 = uint32_t(c0 & 31);
-        sh[bnd] = (s0 + 31u) & 31u;  // rotate right by s0 - 1: the slice's bits land at positions 1 .. BPT (see below)
-        lowmask[bnd] = (1u << s0) - 1u;
+        sh[bnd] = select_rotation(s0);  // rotate right by s0 - 1: the slice's bits land at positions 1 .. BPT (see below)
+        lowmask[bnd] = select_low_mask(s0);
     }
 
     // One block: `cur` was loaded during the previous block (or before the loop); the loads of block blk + 1 are issued

@@ -120,6 +120,24 @@ FLB_HD uint32_t top_bits_lane_major_u16(uint32_t le) {
     return (z | (z >> 12)) & 0x11u;
 }
 
+// ---- select (fl_scan.cuh, select_warp_kernel): where a thread's slice of a row sits in the block bitmap --------------------
+// Thread (q, j) holds, for local row i of its run (global row r = q*RPG + i), the BPT = 128/T values of lanes j*BPT .. of
+// that row = BPT CONSECUTIVE original indices starting at index(r, j*BPT).  Rows of one 8-row band share FL_ORDER[r/8], so
+// inside band `band` (rows q*RPG + band*8 + 0..7; RPG < 8: the whole run is one band) the first index is
+// c0 + (i%8)*128: the bitmap word advances by 4 per row and the bit position inside the word is the same for every row.
+template <int TBITS>
+FLB_HD int select_band_origin(int q, int band, int j) {
+    const int RPG = TBITS / 4, BPT = 128 / TBITS;
+    const int r0 = q * RPG + band * 8;  // first global row of the band
+    return scan_fl_order(r0 >> 3) * 16 + (r0 & 7) * 128 + j * BPT;
+}
+// The compaction tests bit k of the slice at register position k + 1 (one R2P then moves bits 1.. into predicates; bit 0
+// would cost two extra instructions): the bitmap word is rotated right by s0 - 1, s0 = position of the slice in the word.
+FLB_HD uint32_t select_rotation(uint32_t s0) { return (s0 + 31u) & 31u; }
+FLB_HD uint32_t select_rotate(uint32_t word, uint32_t rot) { return rot ? ((word >> rot) | (word << (32u - rot))) : word; }
+// mask of the bits of the word that precede the slice: their popcount is the slice's rank offset inside the word
+FLB_HD uint32_t select_low_mask(uint32_t s0) { return (1u << s0) - 1u; }
+
 // first original index (block-local) of lane l's run
 FLB_HD int lane_run_start(int l) { return 64 * (l & 15) + 8 * scan_fl_order(l >> 4); }
 

@@ -116,8 +116,56 @@ static int run_orig(int trials) {
     return bad;
 }
 
+// select: the compaction of select_warp_kernel on an emulated warp.  Values are their own original index, so the staged
+// output must be the ascending list of the selected indices.  Uses the kernel's helpers for the slice position, the
+// rotation that puts bit k of the slice at register position k + 1, and the rank inside the word.
+template <int TBITS>
+static int run_select(int trials) {
+    const int L = 1024 / TBITS, RPG = TBITS / 4, BPT = 128 / TBITS, BANDS = RPG > 8 ? RPG / 8 : 1;
+    int bad = 0;
+    for (int t = 0; t < trials; ++t) {
+        uint32_t bitmap[32];
+        const int density = t % 5;  // 0: empty, 1: sparse, 2: quarter, 3: half, 4: full
+        for (int w = 0; w < 32; ++w) {
+            const uint32_t a = (uint32_t)rnd(), b = (uint32_t)rnd(), c = (uint32_t)rnd();
+            bitmap[w] = density == 0 ? 0u : density == 1 ? (a & b & c & (uint32_t)rnd()) : density == 2 ? (a & b) : density == 3 ? a : ~0u;
+        }
+        uint32_t prefix[32], total = 0;
+        for (int w = 0; w < 32; ++w) { prefix[w] = total; total += (uint32_t)__builtin_popcount(bitmap[w]); }
+        std::vector<int> stage(1024 + 32, -1);
+        for (int th = 0; th < 32; ++th) {
+            const int g = th >> 3, j = th & 7;
+            const int q = (TBITS >= 32) ? (((g << 1) & 2) | (g >> 1)) : g;  // WarpLay<T>::rank_of_group
+            for (int i = 0; i < RPG; ++i) {
+                const int band = BANDS > 1 ? i / 8 : 0;
+                const int c0 = flb::select_band_origin<TBITS>(q, band, j);
+                const int word = (c0 >> 5) + 4 * (i % 8);
+                const uint32_t s0 = uint32_t(c0 & 31);
+                if (int(s0) + BPT > 32 || word > 31) { if (!bad) std::printf("u%d: slice leaves its bitmap word\n", TBITS); ++bad; continue; }
+                const int r = q * RPG + i;
+                const int first = FL_ORDER[r / 8] * 16 + (r % 8) * 128 + j * BPT;  // index(r, j*BPT), macros.rs:20-24
+                if (first != word * 32 + int(s0)) { if (!bad) std::printf("u%d: slice position mismatch\n", TBITS); ++bad; continue; }
+                const uint32_t bits = flb::select_rotate(bitmap[word], flb::select_rotation(s0));
+                uint32_t rank = prefix[word] + (uint32_t)__builtin_popcount(bitmap[word] & flb::select_low_mask(s0));
+                for (int k = 0; k < BPT; ++k)
+                    if (bits & (2u << k)) stage[rank++] = first + k;
+            }
+        }
+        uint32_t n = 0;
+        for (int idx = 0; idx < 1024; ++idx)
+            if (bitmap[idx >> 5] >> (idx & 31) & 1u) { if (stage[n] != idx) { if (!bad) std::printf("u%d trial %d: selected value %u out of order\n", TBITS, t, n); ++bad; break; } ++n; }
+        if (n == total && stage[total] != -1) { if (!bad) std::printf("u%d trial %d: wrote past the selected count\n", TBITS, t); ++bad; }
+        (void)L;
+    }
+    return bad;
+}
+
 int main() {
     int bad = 0;
+    bad += run_select<8>(100);
+    bad += run_select<16>(100);
+    bad += run_select<32>(100);
+    bad += run_select<64>(100);
     // SWAR lane-wise x <= y and the top-bit compression: u8 exhaustive over (x, y) in every lane position with
     // random neighbours; u16 edge values x random
     for (int x = 0; x < 256; ++x)
