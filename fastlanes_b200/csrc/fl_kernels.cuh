@@ -267,6 +267,17 @@ __device__ __forceinline__ void orig_tile_scatter(unsigned char* tile, const Sli
         }
     }
 }
+// A 16-byte shared load the compiler may not narrow.  With u64 at W <= 32 only the low word of every value is live after
+// the delta, and the compiler turns each LDS.128 of the gather below into two LDS.32 (offsets 0 and 8).  A 32-bit access
+// is served for the whole warp at once, and the swizzle — built for 16-byte accesses, which are served per quarter-warp —
+// leaves the four row groups on the same banks: 4 wavefronts per LDS.32 instead of 1, 96 excess wavefronts per block
+// (ncu source page, profiles/ncu_r02_u64_orig.md).  The full 16-byte load costs 4 wavefronts for both words.
+__device__ __forceinline__ uint4 lds128_full(const void* p) {
+    uint4 v;
+    asm volatile("ld.volatile.shared.v4.u32 {%0,%1,%2,%3}, [%4];" : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "r"(smem_addr(p)) : "memory");
+    return v;
+}
+
 // inverse: shared tile in ORIGINAL order -> register tile
 template <class T, int RPG>
 __device__ __forceinline__ void orig_tile_gather(const unsigned char* tile, Slice<T> (&v)[RPG], int q, int j) {
@@ -277,8 +288,11 @@ __device__ __forceinline__ void orig_tile_gather(const unsigned char* tile, Slic
         for (int r = 0; r < NR; ++r) {
             const int A0 = orig_run_byte_offset<T>(q, j, r);
 #pragma unroll
-            for (int m = 0; m < RPG / EPC; ++m)
-                scatter_rows_chunk<T, RPG>(v, r, m, *reinterpret_cast<const uint4*>(tile + orig_tile_swizzle<T>(A0 + m * 16)));
+            for (int m = 0; m < RPG / EPC; ++m) {
+                const unsigned char* src = tile + orig_tile_swizzle<T>(A0 + m * 16);
+                if constexpr (sizeof(T) == 8) scatter_rows_chunk<T, RPG>(v, r, m, lds128_full(src));
+                else scatter_rows_chunk<T, RPG>(v, r, m, *reinterpret_cast<const uint4*>(src));
+            }
         }
     } else if constexpr (sizeof(T) == 2) {
 #pragma unroll
