@@ -618,7 +618,10 @@ pack_warp_kernel(const char* __restrict__ in, char* __restrict__ packed, size_t 
             const unsigned char* sp = tma_in + j * 16;
             seq_rows<RPG>([&](auto ic) {
                 constexpr int i = decltype(ic)::value;
-                src[i] = to_slice<T>(*reinterpret_cast<const uint4*>(sp + warp_row_offset<T, i, LINEAR>(q)));
+                // u64: whole 16-byte loads even where only the low words are live (W <= 32) — narrowed to LDS.32 they
+                // conflict 4-way across the row groups (see lds128_full)
+                if constexpr (sizeof(T) == 8) src[i] = to_slice<T>(lds128_full(sp + warp_row_offset<T, i, LINEAR>(q)));
+                else src[i] = to_slice<T>(*reinterpret_cast<const uint4*>(sp + warp_row_offset<T, i, LINEAR>(q)));
             });
         } else {
             seq_rows<RPG>([&](auto ic) {
