@@ -36,6 +36,8 @@ def main():
         "transpose_delta_pack": lambda: _lib.fn("fl_transpose_delta_pack", tb)(w, n, U, B, P, sp),
         "for_pack_auto": lambda: _lib.fn("fl_for_pack_auto", tb)(w, n, U, B, None, P, sp),
         "for_pack": lambda: _lib.fn("fl_for_pack", tb)(w, n, U, 12345 % (1 << tb), P, sp),
+        "unfor_pack": lambda: _lib.fn("fl_unfor_pack", tb)(w, n, P, 12345 % (1 << tb), U, sp),
+        "undelta_pack_filter": lambda: _lib.fn("fl_undelta_pack_filter", tb)(w, n, P, B, ((1 << tb) - 1) // 4, ((1 << tb) - 1) // 2, bm.data_ptr(), cnt.data_ptr(), sp),
         "unpack_filter": lambda: _lib.fn("fl_unpack_filter", tb)(w, n, P, None, 0, m // 4, m // 2, bm.data_ptr(), cnt.data_ptr(), sp),
     }
     if op == "unpack_select":  # value-independent bitmap, ~25 % selected, + the exclusive prefix of the block counts
