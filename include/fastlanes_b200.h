@@ -17,10 +17,14 @@
  *                          passed as void*; NULL = the legacy default stream).  Pointers must be
  *                          16-byte aligned (cudaMalloc gives 256) else FL_ERR_ALIGN.  Nothing is
  *                          allocated, nothing is retained after the stream reaches the call.
- *       fl_host_<op>_<T>   HOST pointers, synchronous: H2D copy, kernels, D2H copy, chunked and
- *                          pipelined over internal streams on the current CUDA device.  With
- *                          n_blocks = 1 these are the reference's single-block trait calls.
- *                          Page-locked buffers (fl_host_alloc / fl_host_register) copy faster.
+ *       fl_host_<op>_<T>   HOST pointers, synchronous, on the current CUDA device.  With n_blocks = 1
+ *                          these are the reference's single-block trait calls.  Three paths, same
+ *                          bytes: calls up to 256 KiB go through a page-locked bounce buffer the
+ *                          kernel addresses directly (one launch); calls whose buffers are ALL
+ *                          page-locked (fl_host_alloc / fl_host_register / cudaHostAlloc) and that
+ *                          move at most FLB_DIRECT_MAX bytes (default 512 MiB) run as one launch on
+ *                          the caller's memory; everything else is chunked H2D copy / kernel / D2H
+ *                          copy pipelined over internal streams.
  *   - Input and output must not overlap (Rust's & / &mut guarantee in the reference).
  *   - No entry point unwinds, aborts or falls back to the CPU: without a usable CUDA device every
  *     call returns FL_ERR_CUDA.  Thread-safe; fl_last_error_string() is thread-local.
