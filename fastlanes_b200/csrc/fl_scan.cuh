@@ -11,7 +11,8 @@
 //                        in index order (stream compaction given the exclusive prefix of the block counts)
 //                        reads 128*W + 128 + 8, writes sizeof(T) * selected bytes per block
 //
-// Both reuse warp_decode_tile (the decode core of unpack_warp_kernel), one warp = one block.  Bit i of a block
+// Both reuse the decode core of unpack_warp_kernel (warp_run_from / warp_extract_rows), one warp = one block at a time, 1-8
+// consecutive blocks per warp with the loads of the next block issued ahead (RunLoads below).  Bit i of a block
 // refers to the ORIGINAL value index i of the unpacked vector, i.e. exactly the element `output[i]` that
 // BitPacking::unpack would have produced (index(row,lane), src/macros.rs:20-24); the bitmap is little-endian
 // (byte i/8, bit i%8), the layout of an Arrow validity/selection buffer.
