@@ -13,9 +13,15 @@
 //!  * the **`device` module** exposes the batched, stream-ordered entry points on device pointers,
 //!    which is where the throughput is (a whole column chunk per call, data resident in HBM).
 //!
-//! Unlike the reference, the const-generic `W` forms need no `generic_const_exprs`: the packed
-//! length is checked at run time against `1024 * W / T`.
+//! Unlike the reference, the const-generic `W` forms of the default traits need no `generic_const_exprs`:
+//! the packed length is checked at run time against `1024 * W / T`.  Callers that want the reference's
+//! signatures to the letter (`&mut [Self; 1024 * W / Self::T]`, `BitPackWidth<W>: SupportedBitPackWidth<Self>`)
+//! enable the cargo feature `nightly-exact` and `use fastlanes_b200::exact::{BitPacking, Delta, FoR, Transpose}`.
 #![allow(clippy::missing_safety_doc)]
+// `exact` (feature "nightly-exact"): the reference's own signatures, array-typed packed operands included.  They need the
+// same nightly feature the reference itself is built with (src/lib.rs:2 there, rust-toolchain.toml).
+#![cfg_attr(feature = "nightly-exact", allow(incomplete_features))]
+#![cfg_attr(feature = "nightly-exact", feature(generic_const_exprs))]
 
 use core::ffi::c_void;
 
@@ -178,6 +184,136 @@ bind_type!(u32, fl_host_pack_u32, fl_host_unpack_u32, fl_host_unpack_single_u32,
            fl_host_delta_u32, fl_host_undelta_u32, fl_host_undelta_pack_u32, fl_host_transpose_u32, fl_host_untranspose_u32);
 bind_type!(u64, fl_host_pack_u64, fl_host_unpack_u64, fl_host_unpack_single_u64, fl_host_for_pack_u64, fl_host_unfor_pack_u64,
            fl_host_delta_u64, fl_host_undelta_u64, fl_host_undelta_pack_u64, fl_host_transpose_u64, fl_host_untranspose_u64);
+
+/// The reference's EXACT trait signatures (src/bitpacking.rs:8-59, src/delta.rs:6-17, src/ffor.rs:4-18,
+/// src/transpose.rs:4-7 of spiraldb/fastlanes 0.1.8): packed operands are `[Self; 1024 * W / Self::T]` arrays and the
+/// width is bounded at compile time, so existing call sites compile unchanged.  Every method forwards to the
+/// slice-based impls above, i.e. to the same `fl_host_*` calls.  Never compiled in this repository (no Rust toolchain).
+#[cfg(feature = "nightly-exact")]
+pub mod exact {
+    use core::mem::size_of;
+
+    pub use super::{transpose, FastLanes, FL_ORDER};
+
+    pub struct Pred<const B: bool>;
+    pub trait Satisfied {}
+    impl Satisfied for Pred<true> {}
+
+    pub struct BitPackWidth<const W: usize>;
+    pub trait SupportedBitPackWidth<T> {}
+    impl<const W: usize, T> SupportedBitPackWidth<T> for BitPackWidth<W> where Pred<{ W <= 8 * size_of::<T>() }>: Satisfied {}
+
+    pub trait BitPacking: FastLanes {
+        fn pack<const W: usize>(input: &[Self; 1024], output: &mut [Self; 1024 * W / Self::T])
+        where
+            BitPackWidth<W>: SupportedBitPackWidth<Self>;
+        unsafe fn unchecked_pack(width: usize, input: &[Self], output: &mut [Self]);
+        fn unpack<const W: usize>(input: &[Self; 1024 * W / Self::T], output: &mut [Self; 1024])
+        where
+            BitPackWidth<W>: SupportedBitPackWidth<Self>;
+        unsafe fn unchecked_unpack(width: usize, input: &[Self], output: &mut [Self]);
+        fn unpack_single<const W: usize>(packed: &[Self; 1024 * W / Self::T], index: usize) -> Self
+        where
+            BitPackWidth<W>: SupportedBitPackWidth<Self>;
+        unsafe fn unchecked_unpack_single(width: usize, input: &[Self], index: usize) -> Self;
+    }
+
+    pub trait FoR: BitPacking {
+        fn for_pack<const W: usize>(input: &[Self; 1024], reference: Self, output: &mut [Self; 1024 * W / Self::T])
+        where
+            BitPackWidth<W>: SupportedBitPackWidth<Self>;
+        fn unfor_pack<const W: usize>(input: &[Self; 1024 * W / Self::T], reference: Self, output: &mut [Self; 1024])
+        where
+            BitPackWidth<W>: SupportedBitPackWidth<Self>;
+    }
+
+    pub trait Delta: BitPacking {
+        fn delta(input: &[Self; 1024], base: &[Self; Self::LANES], output: &mut [Self; 1024]);
+        fn undelta(input: &[Self; 1024], base: &[Self; Self::LANES], output: &mut [Self; 1024]);
+        fn undelta_pack<const W: usize>(input: &[Self; 1024 * W / Self::T], base: &[Self; Self::LANES], output: &mut [Self; 1024])
+        where
+            BitPackWidth<W>: SupportedBitPackWidth<Self>;
+    }
+
+    pub trait Transpose: FastLanes {
+        fn transpose(input: &[Self; 1024], output: &mut [Self; 1024]);
+        fn untranspose(input: &[Self; 1024], output: &mut [Self; 1024]);
+    }
+
+    macro_rules! exact_impl {
+        ($T:ty) => {
+            impl BitPacking for $T {
+                fn pack<const W: usize>(input: &[Self; 1024], output: &mut [Self; 1024 * W / Self::T])
+                where
+                    BitPackWidth<W>: SupportedBitPackWidth<Self>,
+                {
+                    <$T as super::BitPacking>::pack::<W>(input, &mut output[..])
+                }
+                unsafe fn unchecked_pack(width: usize, input: &[Self], output: &mut [Self]) {
+                    <$T as super::BitPacking>::unchecked_pack(width, input, output)
+                }
+                fn unpack<const W: usize>(input: &[Self; 1024 * W / Self::T], output: &mut [Self; 1024])
+                where
+                    BitPackWidth<W>: SupportedBitPackWidth<Self>,
+                {
+                    <$T as super::BitPacking>::unpack::<W>(&input[..], output)
+                }
+                unsafe fn unchecked_unpack(width: usize, input: &[Self], output: &mut [Self]) {
+                    <$T as super::BitPacking>::unchecked_unpack(width, input, output)
+                }
+                fn unpack_single<const W: usize>(packed: &[Self; 1024 * W / Self::T], index: usize) -> Self
+                where
+                    BitPackWidth<W>: SupportedBitPackWidth<Self>,
+                {
+                    <$T as super::BitPacking>::unpack_single::<W>(&packed[..], index)
+                }
+                unsafe fn unchecked_unpack_single(width: usize, input: &[Self], index: usize) -> Self {
+                    <$T as super::BitPacking>::unchecked_unpack_single(width, input, index)
+                }
+            }
+            impl FoR for $T {
+                fn for_pack<const W: usize>(input: &[Self; 1024], reference: Self, output: &mut [Self; 1024 * W / Self::T])
+                where
+                    BitPackWidth<W>: SupportedBitPackWidth<Self>,
+                {
+                    <$T as super::FoR>::for_pack::<W>(input, reference, &mut output[..])
+                }
+                fn unfor_pack<const W: usize>(input: &[Self; 1024 * W / Self::T], reference: Self, output: &mut [Self; 1024])
+                where
+                    BitPackWidth<W>: SupportedBitPackWidth<Self>,
+                {
+                    <$T as super::FoR>::unfor_pack::<W>(&input[..], reference, output)
+                }
+            }
+            impl Delta for $T {
+                fn delta(input: &[Self; 1024], base: &[Self; Self::LANES], output: &mut [Self; 1024]) {
+                    <$T as super::Delta>::delta(input, &base[..], output)
+                }
+                fn undelta(input: &[Self; 1024], base: &[Self; Self::LANES], output: &mut [Self; 1024]) {
+                    <$T as super::Delta>::undelta(input, &base[..], output)
+                }
+                fn undelta_pack<const W: usize>(input: &[Self; 1024 * W / Self::T], base: &[Self; Self::LANES], output: &mut [Self; 1024])
+                where
+                    BitPackWidth<W>: SupportedBitPackWidth<Self>,
+                {
+                    <$T as super::Delta>::undelta_pack::<W>(&input[..], &base[..], output)
+                }
+            }
+            impl Transpose for $T {
+                fn transpose(input: &[Self; 1024], output: &mut [Self; 1024]) {
+                    <$T as super::Transpose>::transpose(input, output)
+                }
+                fn untranspose(input: &[Self; 1024], output: &mut [Self; 1024]) {
+                    <$T as super::Transpose>::untranspose(input, output)
+                }
+            }
+        };
+    }
+    exact_impl!(u8);
+    exact_impl!(u16);
+    exact_impl!(u32);
+    exact_impl!(u64);
+}
 
 /// Batched, stream-ordered entry points on DEVICE pointers (the throughput path).
 /// `stream` is a `cudaStream_t`; null = the legacy default stream.  Pointers must be 16-byte aligned.
